@@ -1,0 +1,75 @@
+"""ctypes binding of libsdvg.so (include/sdvg.h).  No torch types cross this boundary: only raw device
+pointers, sizes and the CUDA stream handle.  There is no CPU fallback: if the shared library cannot be
+loaded, or no sm_100 device is present, the errors propagate as RuntimeError."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdvg.so")
+
+PRECISIONS = {"fp32_simt": 0, "fp32": 1, "fp16": 2, "bf16": 3, "mixed": 4}
+KERNEL_CLASSES = ("gemm_tc", "gemm_simt", "attention", "layernorm", "pack")
+
+# every symbol include/sdvg.h declares (tests check the library exports all of them)
+SYMBOLS = (
+    "sdvg_version", "sdvg_last_error", "sdvg_create", "sdvg_destroy", "sdvg_workspace_bytes", "sdvg_set_weight",
+    "sdvg_num_weights", "sdvg_weight_key", "sdvg_finalize_weights", "sdvg_forward", "sdvg_rollout",
+    "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm",
+)
+
+
+class SdvgConfig(C.Structure):
+    _fields_ = [("dim_model", C.c_int32), ("num_heads", C.c_int32), ("num_encoder_layers", C.c_int32),
+                ("num_decoder_layers", C.c_int32), ("latent_dim", C.c_int32), ("dim_feedforward", C.c_int32),
+                ("layer_norm_eps", C.c_float), ("max_clips", C.c_int32), ("max_tokens", C.c_int32),
+                ("max_history", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32)]
+
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Load (building first if the in-tree .so is missing or stale and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python sd-video-gen_b200/build.py` "
+                           "(libsdvg has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    lib.sdvg_version.restype = C.c_int
+    lib.sdvg_last_error.restype = C.c_char_p
+    lib.sdvg_last_error.argtypes = [vp]
+    lib.sdvg_create.argtypes = [C.POINTER(SdvgConfig), C.POINTER(vp)]
+    lib.sdvg_destroy.argtypes = [vp]
+    lib.sdvg_destroy.restype = None
+    lib.sdvg_workspace_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.sdvg_set_weight.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_int64), i32]
+    lib.sdvg_num_weights.argtypes = [vp]
+    lib.sdvg_weight_key.argtypes = [vp, i32]
+    lib.sdvg_weight_key.restype = C.c_char_p
+    lib.sdvg_finalize_weights.argtypes = [vp, vp]
+    lib.sdvg_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.sdvg_rollout.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, f32, f32, vp, vp]
+    lib.sdvg_timing_enable.argtypes = [vp, i32]
+    lib.sdvg_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]
+    lib.sdvg_launch_count.argtypes = [vp]
+    lib.sdvg_launch_count.restype = C.c_int64
+    lib.sdvg_gemm.argtypes = [i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(f32), vp]
+    _lib = lib
+    return lib
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = load().sdvg_last_error(handle)
+        raise RuntimeError(f"libsdvg error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,146 @@
+// K2 - fused multi-head attention for very short sequences (S <= 32 tokens; the path uses 5, 6 or 10).
+// softmax(Q K^T / sqrt(hd) + mask) V per (clip, head), i.e. the scaled_dot_product_attention inside
+// torch.nn.MultiheadAttention as called by the layers constructed at models/transformer.py:38-44.
+//
+// One warp per (clip, head): the head dimension is spread over the lanes (128-bit loads when hd % 128 == 0),
+// scores are lane-partial dot products reduced with shuffles, softmax runs in registers in fp32 (the layer-0
+// scores are near one-hot because emb*sqrt(d) is un-normalised - SURVEY.md fact 6 - so nothing here is 16-bit),
+// K/V rows are re-read from L1.  HBM-bound: bytes = (Sq + 2 Sk) hd 4 in, Sq hd (2..8) out per (clip, head).
+// Mask kinds: 0 none, 1 causal (key <= query; models/transformer.py:70-89 without materialising the matrix),
+// 2 additive fp32 (Sq x Sk) as passed to forward(..., tgt_mask).
+#pragma once
+#include "common.cuh"
+
+namespace sdvg {
+
+constexpr int kAttnMaxS = 32;
+
+struct AttnArgs {
+  const float* q; int ldq;
+  const float* k; const float* v; int ldkv;
+  int clips, heads, hd, Sq, Sk;
+  int mask_kind; const float* mask;
+  float scale;
+  int q_first;        // first query row to compute (Sq-1 when only the last token is needed)
+  float* out32; int ld32;
+  uint16_t* out_hi; uint16_t* out_lo; int ld16; int bf16;
+};
+
+// Lane-distributed row fragment: element index of (chunk c, lane, v) is (c*32 + lane)*VEC + v.
+template <int VEC, int NCH>
+__device__ __forceinline__ void load_frag(float (&f)[NCH * VEC], const float* __restrict__ row, int hd, int lane) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int e0 = (c * 32 + lane) * VEC;
+    if constexpr (VEC == 4) {
+      const float4 t = e0 < hd ? __ldg(reinterpret_cast<const float4*>(row + e0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      f[c * 4 + 0] = t.x; f[c * 4 + 1] = t.y; f[c * 4 + 2] = t.z; f[c * 4 + 3] = t.w;
+    } else {
+      f[c] = e0 < hd ? __ldg(row + e0) : 0.f;
+    }
+  }
+}
+
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ AttnArgs a) {
+  constexpr int EPL = VEC * NCH;
+  const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= a.clips * a.heads) return;
+  const int b = warp_global / a.heads, h = warp_global - b * a.heads;
+  const int hd = a.hd;
+  const float* qb = a.q + static_cast<size_t>(b) * a.Sq * a.ldq + h * hd;
+  const float* kb = a.k + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
+  const float* vb = a.v + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int i = a.q_first; i < a.Sq; ++i) {
+    float ql[EPL];
+    load_frag<VEC, NCH>(ql, qb + static_cast<size_t>(i) * a.ldq, hd, lane);
+    float sc[kAttnMaxS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kAttnMaxS; ++j) {
+      sc[j] = -INFINITY;
+      if (j < a.Sk) {
+        float kl[EPL];
+        load_frag<VEC, NCH>(kl, kb + static_cast<size_t>(j) * a.ldkv, hd, lane);
+        float part = 0.f;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) part = fmaf(ql[t], kl[t], part);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        float s = part * a.scale;
+        if (a.mask_kind == 1) { if (j > i + (a.Sk - a.Sq)) s = -INFINITY; }
+        else if (a.mask_kind == 2) s += __ldg(a.mask + i * a.Sk + j);
+        sc[j] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kAttnMaxS; ++j) {
+      if (j < a.Sk) { sc[j] = exp2f((sc[j] - mx) * kLog2e); sum += sc[j]; }
+    }
+    const float inv = 1.0f / sum;
+    float ol[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) ol[t] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kAttnMaxS; ++j) {
+      if (j < a.Sk) {
+        const float p = sc[j] * inv;
+        float vl[EPL];
+        load_frag<VEC, NCH>(vl, vb + static_cast<size_t>(j) * a.ldkv, hd, lane);
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) ol[t] = fmaf(p, vl[t], ol[t]);
+      }
+    }
+    const size_t row = static_cast<size_t>(b) * a.Sq + i;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int e0 = (c * 32 + lane) * VEC;
+      if (e0 >= hd) continue;
+      const int col = h * hd + e0;
+      if constexpr (VEC == 4) {
+        if (a.out32)
+          *reinterpret_cast<float4*>(a.out32 + row * a.ld32 + col) =
+              make_float4(ol[c * 4], ol[c * 4 + 1], ol[c * 4 + 2], ol[c * 4 + 3]);
+        if (a.out_hi) {
+          uint16_t hi[4], lo[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) { hi[v] = to_plane_hi(ol[c * 4 + v], a.bf16); lo[v] = to_plane_lo(ol[c * 4 + v], hi[v]); }
+          *reinterpret_cast<uint2*>(a.out_hi + row * a.ld16 + col) =
+              make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+          if (a.out_lo)
+            *reinterpret_cast<uint2*>(a.out_lo + row * a.ld16 + col) =
+                make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+        }
+      } else {
+        const float val = ol[c];
+        if (a.out32) a.out32[row * a.ld32 + col] = val;
+        if (a.out_hi) {
+          const uint16_t hi = to_plane_hi(val, a.bf16);
+          a.out_hi[row * a.ld16 + col] = hi;
+          if (a.out_lo) a.out_lo[row * a.ld16 + col] = to_plane_lo(val, hi);
+        }
+      }
+    }
+  }
+}
+
+inline cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  if (a.Sk > kAttnMaxS || a.Sq > kAttnMaxS || a.hd > 256) return cudaErrorInvalidValue;
+  const int warps = a.clips * a.heads;
+  const int grid = ceil_div(warps, 4);
+  const bool vec = (a.hd % 128 == 0) && (a.ldq % 4 == 0) && (a.ldkv % 4 == 0);
+  if (vec && a.hd == 128) attention_kernel<4, 1><<<grid, 128, 0, stream>>>(a);
+  else if (vec && a.hd == 256) attention_kernel<4, 2><<<grid, 128, 0, stream>>>(a);
+  else if (a.hd <= 32) attention_kernel<1, 1><<<grid, 128, 0, stream>>>(a);
+  else if (a.hd <= 64) attention_kernel<1, 2><<<grid, 128, 0, stream>>>(a);
+  else if (a.hd <= 128) attention_kernel<1, 4><<<grid, 128, 0, stream>>>(a);
+  else attention_kernel<1, 8><<<grid, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace sdvg

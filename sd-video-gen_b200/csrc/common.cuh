@@ -1,0 +1,89 @@
+// Shared types for the sdvg kernels: the GEMM epilogue description and 16-bit plane helpers.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace sdvg {
+
+// Split-operand scale: x ~= hi + lo * 2^-11 with hi, lo fp16 (22 significant bits).
+constexpr float kSplitScale = 2048.0f;
+constexpr float kSplitInv = 1.0f / 2048.0f;
+
+// What every GEMM does to its fp32 accumulator before storing (in this order):
+//   v = acc + bias[col];  v *= alpha;  v += pe[pe_index[row / rows_per_clip]][col];  relu;  v += residual[row][col]
+// and where the result goes: an fp32 matrix, and/or 16-bit operand planes (hi and, for split consumers, lo)
+// that the next GEMM reads through TMA.
+struct Epilogue {
+  const float* bias = nullptr;      // [N]
+  float alpha = 1.0f;
+  const float* pe = nullptr;        // [64][ld_pe] positional table (models/positional_encoding.py:17-31)
+  int ld_pe = 0;
+  const int* pe_index = nullptr;    // [clips]; nullptr -> clip index itself
+  int rows_per_clip = 1;
+  int relu = 0;
+  const float* residual = nullptr;  // [M][ld_res]
+  int ld_res = 0;
+  float* out32 = nullptr;           // fp32 output
+  int ld32 = 0;
+  uint16_t* out_hi = nullptr;       // 16-bit planes [M][ld16]
+  uint16_t* out_lo = nullptr;
+  int ld16 = 0;
+  int bf16 = 0;                     // hi plane is bf16 instead of fp16 (lo plane is always fp16)
+  // row mapping of the fp32 output (planes always use identity):
+  //   0 identity;  1 clip-major (b*S+s) -> sequence-major (s*B+b), the reference's (S,B,E) return layout
+  //   (models/transformer.py:60-68);  2 only the last token of every clip is written, to row b
+  //   (prediction/predict.py:42 keeps pred[:, -1]).
+  int row_map = 0;
+  int clips = 0;
+};
+
+__device__ __forceinline__ int epi_out_row(const Epilogue& e, int row) {
+  if (e.row_map == 0) return row;
+  const int b = row / e.rows_per_clip, s = row - b * e.rows_per_clip;
+  if (e.row_map == 1) return s * e.clips + b;
+  return (s == e.rows_per_clip - 1) ? b : -1;
+}
+
+// Row-dependent part resolved once per row: which PE row this token's clip uses (-1: none).
+__device__ __forceinline__ int epi_pe_row(const Epilogue& e, int row) {
+  if (!e.pe) return -1;
+  const int b = row / e.rows_per_clip;
+  return e.pe_index ? __ldg(e.pe_index + b) : b;
+}
+
+__device__ __forceinline__ float epi_value(const Epilogue& e, float acc, int row, int col, int pe_row) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + col);
+  v *= e.alpha;
+  if (pe_row >= 0) v += __ldg(e.pe + static_cast<size_t>(pe_row) * e.ld_pe + col);
+  if (e.relu) v = fmaxf(v, 0.0f);
+  if (e.residual) v += __ldg(e.residual + static_cast<size_t>(row) * e.ld_res + col);
+  return v;
+}
+
+// 16-bit plane conversions ---------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t to_plane_hi(float v, int bf16) {
+  if (bf16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
+}
+// lo plane (split mode, fp16 only): lo = fp16((v - hi) * 2^11)
+__device__ __forceinline__ uint16_t to_plane_lo(float v, uint16_t hi) {
+  const float r = (v - __half2float(__ushort_as_half(hi))) * kSplitScale;
+  return __half_as_ushort(__float2half_rn(r));
+}
+
+// Store one value to all requested destinations (scalar path).
+__device__ __forceinline__ void epi_store(const Epilogue& e, float v, int row, int out_row, int col) {
+  if (e.out32 && out_row >= 0) e.out32[static_cast<size_t>(out_row) * e.ld32 + col] = v;
+  if (e.out_hi) {
+    const uint16_t h = to_plane_hi(v, e.bf16);
+    e.out_hi[static_cast<size_t>(row) * e.ld16 + col] = h;
+    if (e.out_lo) e.out_lo[static_cast<size_t>(row) * e.ld16 + col] = to_plane_lo(v, h);
+  }
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace sdvg

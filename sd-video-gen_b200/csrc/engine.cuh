@@ -1,0 +1,716 @@
+// Host-side engine behind the C ABI (include/sdvg.h): owns packed weights + workspace and sequences the
+// sm_100a kernels for one forward pass (models/transformer.py:47-68 -> torch.nn.Transformer) and for the
+// autoregressive rollout (prediction/predict.py:16-42,143-197).  No allocation, no host<->device copy and
+// no synchronisation on the hot path.
+#pragma once
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sdvg.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "layernorm.cuh"
+#include "pack.cuh"
+
+namespace sdvg {
+
+enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_SIMT = 1, KC_ATTN = 2, KC_LN = 3, KC_PACK = 4 };
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int bn_index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3; }
+constexpr int kBnValues[4] = {32, 64, 128, 256};
+
+// 16-bit operand planes of a matrix [rows][cols] (row pitch ld, zero padded to a multiple of 64 columns so a
+// TMA box never leaves the tensor along K) with their tensor maps.
+struct Planes {
+  uint16_t* hi = nullptr;
+  uint16_t* lo = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  CUtensorMap tm_hi[4], tm_lo[4];  // activations: [0] only (box 128 rows); weights: one per tile width
+};
+
+struct ActBuf {
+  float* f32 = nullptr;
+  int ld32 = 0;
+  Planes p;
+};
+
+struct Linear {
+  int N = 0, K = 0;
+  const float* w32 = nullptr;
+  const float* bias = nullptr;
+  Planes p;
+  bool split = false;
+};
+
+struct LNParam { const float* w = nullptr; const float* b = nullptr; };
+struct AttnWeights { Linear qkv, q, kv, out; };
+struct EncLayer { AttnWeights sa; Linear ff1, ff2; LNParam n1, n2; };
+struct DecLayer { AttnWeights sa, ca; Linear ff1, ff2; LNParam n1, n2, n3; };
+
+struct WeightSlot {
+  std::string key;
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+  size_t count = 0;
+  bool set = false;
+  // GEMM weights only:
+  bool is_matrix = false;
+  bool need_lo = false;
+  uint16_t* hi = nullptr;
+  uint16_t* lo = nullptr;
+  int ld16 = 0;
+};
+
+class Engine {
+ public:
+  sdvg_config cfg{};
+  std::string err;
+  int num_sms = 148;
+  bool finalized = false;
+  bool timing = false;
+  int64_t launches = 0;
+  size_t bytes_owned = 0;
+
+  std::vector<void*> allocs;
+  std::vector<WeightSlot> slots;
+  std::map<std::string, int> slot_of;
+
+  Linear embedding, out_proj;
+  std::vector<EncLayer> enc;
+  std::vector<DecLayer> dec;
+  LNParam enc_norm, dec_norm;
+  const float* pe_table = nullptr;
+
+  int max_rows = 0;
+  ActBuf lat_s, lat_t, emb_s, emb_t, xs, xt, ybuf, qkv, attn, ffh, mem, qc, kvc, fin;
+  float* hist = nullptr;     // rollout history [max_clips][max_history][E]
+  int* pe_mod64 = nullptr;   // [max_clips] b mod 64
+
+  struct TimedSpan { cudaEvent_t a, b; int cls; double flops, bytes; };
+  std::vector<TimedSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double t_ms[SDVG_NUM_KERNEL_CLASSES] = {}, t_flops[SDVG_NUM_KERNEL_CLASSES] = {}, t_bytes[SDVG_NUM_KERNEL_CLASSES] = {};
+  int64_t t_launch[SDVG_NUM_KERNEL_CLASSES] = {};
+
+  int prec() const { return cfg.precision; }
+  bool tc() const { return cfg.precision != SDVG_FP32_SIMT; }
+  bool bf16() const { return cfg.precision == SDVG_BF16; }
+  bool split_all() const { return cfg.precision == SDVG_FP32; }
+  bool split_first() const { return cfg.precision == SDVG_FP32 || cfg.precision == SDVG_MIXED; }
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  int fail_cuda(cudaError_t e, const char* what) {
+    return fail(SDVG_ERR_CUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+  }
+
+  ~Engine() {
+    for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : event_pool) cudaEventDestroy(e);
+    for (void* p : allocs) cudaFree(p);
+  }
+
+  // ------------------------------------------------------------------ allocation
+  template <typename T>
+  cudaError_t dalloc(T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = count * sizeof(T) < 256 ? 256 : count * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return e;
+    allocs.push_back(p);
+    bytes_owned += bytes;
+    *out = static_cast<T*>(p);
+    return cudaSuccess;
+  }
+
+  cudaError_t alloc_planes(Planes& p, int rows, int cols, bool lo, bool weight) {
+    p.rows = rows; p.cols = cols; p.ld = round_up(cols, kTcBK);
+    cudaError_t e = dalloc(&p.hi, static_cast<size_t>(rows) * p.ld);
+    if (e != cudaSuccess) return e;
+    if (lo) { e = dalloc(&p.lo, static_cast<size_t>(rows) * p.ld); if (e != cudaSuccess) return e; }
+    (void)weight;
+    return cudaSuccess;
+  }
+  bool map_planes(Planes& p, bool weight) {
+    // lo planes are always fp16; hi planes follow the mode
+    if (!weight) {
+      if (!make_tmap_2d(&p.tm_hi[0], p.hi, p.rows, p.ld, p.ld, kTcBM, bf16())) return false;
+      if (p.lo && !make_tmap_2d(&p.tm_lo[0], p.lo, p.rows, p.ld, p.ld, kTcBM, false)) return false;
+      return true;
+    }
+    for (int i = 0; i < 4; ++i) {
+      if (kBnValues[i] > p.rows && i > 0) { p.tm_hi[i] = p.tm_hi[i - 1]; p.tm_lo[i] = p.tm_lo[i - 1]; continue; }
+      const int box = kBnValues[i] > p.rows ? p.rows : kBnValues[i];
+      if (!make_tmap_2d(&p.tm_hi[i], p.hi, p.rows, p.ld, p.ld, box, bf16())) return false;
+      if (p.lo && !make_tmap_2d(&p.tm_lo[i], p.lo, p.rows, p.ld, p.ld, box, false)) return false;
+    }
+    return true;
+  }
+
+  cudaError_t alloc_act(ActBuf& a, int cols, bool f32, bool planes, bool lo) {
+    if (f32) {
+      a.ld32 = cols;
+      cudaError_t e = dalloc(&a.f32, static_cast<size_t>(max_rows) * cols);
+      if (e != cudaSuccess) return e;
+    }
+    if (planes) {
+      cudaError_t e = alloc_planes(a.p, max_rows, cols, lo, false);
+      if (e != cudaSuccess) return e;
+      if (!map_planes(a.p, false)) return cudaErrorUnknown;
+    }
+    return cudaSuccess;
+  }
+
+  int add_slot(const std::string& key, std::vector<int64_t> shape, bool is_matrix, bool need_lo) {
+    WeightSlot s;
+    s.key = key; s.shape = shape; s.count = 1;
+    for (auto v : shape) s.count *= static_cast<size_t>(v);
+    s.is_matrix = is_matrix; s.need_lo = need_lo;
+    slots.push_back(s);
+    slot_of[key] = static_cast<int>(slots.size()) - 1;
+    return static_cast<int>(slots.size()) - 1;
+  }
+
+  // ------------------------------------------------------------------ construction
+  int init(const sdvg_config& c) {
+    cfg = c;
+    const int d = c.dim_model, H = c.num_heads, E = c.latent_dim, ff = c.dim_feedforward;
+    if (d <= 0 || H <= 0 || d % H != 0 || E <= 0 || ff <= 0 || c.num_encoder_layers < 0 || c.num_decoder_layers < 0)
+      return fail(SDVG_ERR_INVALID, "bad architecture (d=%d H=%d E=%d ff=%d)", d, H, E, ff);
+    if (d % 8 != 0 || E % 8 != 0 || ff % 8 != 0 || d > 4096 || d / H > 256)
+      return fail(SDVG_ERR_UNSUPPORTED, "need d, E, ff multiples of 8, d <= 4096, head dim <= 256");
+    if (c.max_clips <= 0 || c.max_tokens <= 0 || c.max_tokens > kAttnMaxS)
+      return fail(SDVG_ERR_INVALID, "max_clips > 0 and 0 < max_tokens <= %d required", kAttnMaxS);
+    if (c.precision < SDVG_FP32_SIMT || c.precision > SDVG_MIXED) return fail(SDVG_ERR_INVALID, "bad precision");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      return fail(SDVG_ERR_CUDA, "no CUDA device (%s); libsdvg has no CPU fallback", cudaGetErrorString(e));
+    if (c.device < 0 || c.device >= ndev) return fail(SDVG_ERR_INVALID, "device %d out of range", c.device);
+    if ((e = cudaSetDevice(c.device)) != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, c.device)) != cudaSuccess) return fail_cuda(e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+      return fail(SDVG_ERR_CUDA, "device is sm_%d%d; libsdvg is built for sm_100a (B200) only", prop.major, prop.minor);
+    num_sms = prop.multiProcessorCount;
+    if (tc() && !get_encode_fn()) return fail(SDVG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+    // ---- weights registry (keys = the reference's state_dict)
+    const bool sa = split_all(), sf = split_first();
+    add_slot("embedding.weight", {d, E}, true, sf);
+    add_slot("embedding.bias", {d}, false, false);
+    add_slot("positional_encoder.pos_encoding", {64, 1, d}, false, false);
+    auto add_attn = [&](const std::string& p, bool lo_qkv) {
+      add_slot(p + "in_proj_weight", {3 * d, d}, true, lo_qkv);
+      add_slot(p + "in_proj_bias", {3 * d}, false, false);
+      add_slot(p + "out_proj.weight", {d, d}, true, sa);
+      add_slot(p + "out_proj.bias", {d}, false, false);
+    };
+    auto add_ffn_norms = [&](const std::string& p, int norms) {
+      add_slot(p + "linear1.weight", {ff, d}, true, sa);
+      add_slot(p + "linear1.bias", {ff}, false, false);
+      add_slot(p + "linear2.weight", {d, ff}, true, sa);
+      add_slot(p + "linear2.bias", {d}, false, false);
+      for (int n = 1; n <= norms; ++n) {
+        add_slot(p + "norm" + std::to_string(n) + ".weight", {d}, false, false);
+        add_slot(p + "norm" + std::to_string(n) + ".bias", {d}, false, false);
+      }
+    };
+    for (int l = 0; l < c.num_encoder_layers; ++l) {
+      const std::string p = "transformer.encoder.layers." + std::to_string(l) + ".";
+      add_attn(p + "self_attn.", sa || (sf && l == 0));
+      add_ffn_norms(p, 2);
+    }
+    add_slot("transformer.encoder.norm.weight", {d}, false, false);
+    add_slot("transformer.encoder.norm.bias", {d}, false, false);
+    for (int l = 0; l < c.num_decoder_layers; ++l) {
+      const std::string p = "transformer.decoder.layers." + std::to_string(l) + ".";
+      add_attn(p + "self_attn.", sa || (sf && l == 0));
+      add_attn(p + "multihead_attn.", sa);
+      add_ffn_norms(p, 3);
+    }
+    add_slot("transformer.decoder.norm.weight", {d}, false, false);
+    add_slot("transformer.decoder.norm.bias", {d}, false, false);
+    add_slot("out.weight", {E, d}, true, sa);
+    add_slot("out.bias", {E}, false, false);
+
+    for (auto& s : slots) {
+      if ((e = dalloc(&s.dev, s.count)) != cudaSuccess) return fail_cuda(e, "weight alloc");
+      if (s.is_matrix && tc()) {
+        const int rows = static_cast<int>(s.shape[0]), cols = static_cast<int>(s.shape[1]);
+        s.ld16 = round_up(cols, kTcBK);
+        if ((e = dalloc(&s.hi, static_cast<size_t>(rows) * s.ld16)) != cudaSuccess) return fail_cuda(e, "plane alloc");
+        if (s.need_lo && (e = dalloc(&s.lo, static_cast<size_t>(rows) * s.ld16)) != cudaSuccess)
+          return fail_cuda(e, "plane alloc");
+      }
+    }
+
+    // ---- views
+    auto W = [&](const std::string& k) -> WeightSlot& { return slots[slot_of.at(k)]; };
+    auto make_linear = [&](Linear& L, const std::string& wkey, const std::string& bkey, int row0, int nrows) -> bool {
+      WeightSlot& w = W(wkey);
+      const int K = static_cast<int>(w.shape[1]);
+      L.N = nrows; L.K = K;
+      L.w32 = w.dev + static_cast<size_t>(row0) * K;
+      L.bias = W(bkey).dev + row0;
+      L.split = w.need_lo;
+      if (tc()) {
+        L.p.rows = nrows; L.p.cols = K; L.p.ld = w.ld16;
+        L.p.hi = w.hi + static_cast<size_t>(row0) * w.ld16;
+        L.p.lo = w.lo ? w.lo + static_cast<size_t>(row0) * w.ld16 : nullptr;
+        if (!map_planes(L.p, true)) return false;
+      }
+      return true;
+    };
+    auto make_attn = [&](AttnWeights& a, const std::string& p) -> bool {
+      return make_linear(a.qkv, p + "in_proj_weight", p + "in_proj_bias", 0, 3 * d) &&
+             make_linear(a.q, p + "in_proj_weight", p + "in_proj_bias", 0, d) &&
+             make_linear(a.kv, p + "in_proj_weight", p + "in_proj_bias", d, 2 * d) &&
+             make_linear(a.out, p + "out_proj.weight", p + "out_proj.bias", 0, d);
+    };
+    auto ln = [&](const std::string& p) { return LNParam{W(p + ".weight").dev, W(p + ".bias").dev}; };
+    bool ok = make_linear(embedding, "embedding.weight", "embedding.bias", 0, d) &&
+              make_linear(out_proj, "out.weight", "out.bias", 0, E);
+    enc.resize(c.num_encoder_layers);
+    dec.resize(c.num_decoder_layers);
+    for (int l = 0; l < c.num_encoder_layers && ok; ++l) {
+      const std::string p = "transformer.encoder.layers." + std::to_string(l) + ".";
+      ok = make_attn(enc[l].sa, p + "self_attn.") && make_linear(enc[l].ff1, p + "linear1.weight", p + "linear1.bias", 0, ff) &&
+           make_linear(enc[l].ff2, p + "linear2.weight", p + "linear2.bias", 0, d);
+      enc[l].n1 = ln(p + "norm1"); enc[l].n2 = ln(p + "norm2");
+    }
+    for (int l = 0; l < c.num_decoder_layers && ok; ++l) {
+      const std::string p = "transformer.decoder.layers." + std::to_string(l) + ".";
+      ok = make_attn(dec[l].sa, p + "self_attn.") && make_attn(dec[l].ca, p + "multihead_attn.") &&
+           make_linear(dec[l].ff1, p + "linear1.weight", p + "linear1.bias", 0, ff) &&
+           make_linear(dec[l].ff2, p + "linear2.weight", p + "linear2.bias", 0, d);
+      dec[l].n1 = ln(p + "norm1"); dec[l].n2 = ln(p + "norm2"); dec[l].n3 = ln(p + "norm3");
+    }
+    if (!ok) return fail(SDVG_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix");
+    enc_norm = ln("transformer.encoder.norm");
+    dec_norm = ln("transformer.decoder.norm");
+    pe_table = W("positional_encoder.pos_encoding").dev;
+
+    // ---- workspace
+    max_rows = round_up(c.max_clips * c.max_tokens, kTcBM);
+    const bool T = tc(), S = !T;
+#define SDVG_ACT(buf, cols, f32, planes, lo) \
+  if ((e = alloc_act(buf, cols, f32, planes, lo)) != cudaSuccess) return fail_cuda(e, "workspace alloc " #buf)
+    SDVG_ACT(lat_s, E, S, T, sf);
+    SDVG_ACT(lat_t, E, S, T, sf);
+    SDVG_ACT(emb_s, d, true, T, sf);
+    SDVG_ACT(emb_t, d, true, T, sf);
+    SDVG_ACT(xs, d, true, T, sa);
+    SDVG_ACT(xt, d, true, T, sa);
+    SDVG_ACT(ybuf, d, true, false, false);
+    SDVG_ACT(qkv, 3 * d, true, false, false);
+    SDVG_ACT(attn, d, S, T, sa);
+    SDVG_ACT(ffh, ff, S, T, sa);
+    SDVG_ACT(mem, d, S, T, sa);
+    SDVG_ACT(qc, d, true, false, false);
+    SDVG_ACT(kvc, 2 * d, true, false, false);
+    SDVG_ACT(fin, d, S, T, sa);
+#undef SDVG_ACT
+    if (c.max_history > 0 &&
+        (e = dalloc(&hist, static_cast<size_t>(c.max_clips) * c.max_history * E)) != cudaSuccess)
+      return fail_cuda(e, "history alloc");
+    std::vector<int> mod(c.max_clips);
+    for (int i = 0; i < c.max_clips; ++i) mod[i] = i % 64;
+    if ((e = dalloc(&pe_mod64, static_cast<size_t>(c.max_clips))) != cudaSuccess) return fail_cuda(e, "pe alloc");
+    if ((e = cudaMemcpy(pe_mod64, mod.data(), mod.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail_cuda(e, "pe copy");
+    return SDVG_OK;
+  }
+
+  // ------------------------------------------------------------------ weights
+  int set_weight(const char* key, const void* data, const int64_t* shape, int ndim) {
+    auto it = slot_of.find(key ? key : "");
+    if (it == slot_of.end()) return fail(SDVG_ERR_INVALID, "unknown state_dict key '%s'", key ? key : "(null)");
+    WeightSlot& s = slots[it->second];
+    if (ndim != static_cast<int>(s.shape.size())) return fail(SDVG_ERR_INVALID, "'%s': rank %d, expected %zu", key, ndim, s.shape.size());
+    for (int i = 0; i < ndim; ++i)
+      if (shape[i] != s.shape[i]) return fail(SDVG_ERR_INVALID, "'%s': dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)s.shape[i]);
+    cudaError_t e = cudaMemcpy(s.dev, data, s.count * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) return fail_cuda(e, "weight copy");
+    s.set = true;
+    finalized = false;
+    return SDVG_OK;
+  }
+
+  int finalize(cudaStream_t st) {
+    if (finalized) return SDVG_OK;
+    for (auto& s : slots)
+      if (!s.set) return fail(SDVG_ERR_STATE, "weight '%s' was never set", s.key.c_str());
+    if (tc()) {
+      for (auto& s : slots) {
+        if (!s.is_matrix) continue;
+        PackArgs a{};
+        a.src = s.dev; a.src_clip_stride = s.shape[1]; a.src_slot_stride = 0;
+        a.clips = static_cast<int>(s.shape[0]); a.tokens = 1; a.width = static_cast<int>(s.shape[1]);
+        a.slot[0] = 0; a.fill = 0.f; a.scale = 1.f;
+        a.out32 = nullptr; a.out_hi = s.hi; a.out_lo = s.lo; a.ld16 = s.ld16; a.bf16 = bf16();
+        cudaError_t e = launch_pack(a, num_sms, st);
+        ++launches;
+        if (e != cudaSuccess) return fail_cuda(e, "weight pack");
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail_cuda(e, "finalize sync");
+    finalized = true;
+    return SDVG_OK;
+  }
+
+  // ------------------------------------------------------------------ timing
+  struct Scope {
+    Engine* g; cudaStream_t st; bool on; TimedSpan sp;
+    Scope(Engine* g_, int cls, double flops, double bytes, cudaStream_t st_) : g(g_), st(st_), on(g_->timing) {
+      ++g->launches;
+      if (!on) return;
+      sp.cls = cls; sp.flops = flops; sp.bytes = bytes;
+      sp.a = g->get_event(); sp.b = g->get_event();
+      cudaEventRecord(sp.a, st);
+    }
+    ~Scope() {
+      if (!on) return;
+      cudaEventRecord(sp.b, st);
+      g->spans.push_back(sp);
+    }
+  };
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  int timing_read(double* ms, int64_t* n, double* flops, double* bytes) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail_cuda(e, "timing sync");
+    for (auto& s : spans) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, s.a, s.b);
+      t_ms[s.cls] += t; t_flops[s.cls] += s.flops; t_bytes[s.cls] += s.bytes; ++t_launch[s.cls];
+      event_pool.push_back(s.a); event_pool.push_back(s.b);
+    }
+    spans.clear();
+    for (int i = 0; i < SDVG_NUM_KERNEL_CLASSES; ++i) {
+      if (ms) ms[i] = t_ms[i];
+      if (n) n[i] = t_launch[i];
+      if (flops) flops[i] = t_flops[i];
+      if (bytes) bytes[i] = t_bytes[i];
+      t_ms[i] = t_flops[i] = t_bytes[i] = 0; t_launch[i] = 0;
+    }
+    return SDVG_OK;
+  }
+
+  // ------------------------------------------------------------------ kernels
+  // Tile width: trade wave quantisation (tiles vs. SM count) against per-tile efficiency.
+  int choose_bn(int M, int N, bool split) const {
+    static const double tile_eff[4] = {0.45, 0.70, 0.90, 1.0};
+    const int m_tiles = ceil_div(M, kTcBM);
+    int best = 32; double best_score = -1.0;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = kBnValues[i];
+      if (split && bn > 128) continue;
+      if (bn > 32 && bn > N) continue;
+      const int tiles = m_tiles * ceil_div(N, bn);
+      const int waves = ceil_div(tiles, num_sms);
+      const double quant = static_cast<double>(tiles) / (static_cast<double>(waves) * num_sms);
+      const double score = quant * tile_eff[i];
+      if (score > best_score) { best_score = score; best = bn; }
+    }
+    return best;
+  }
+
+  cudaError_t gemm_tc_dispatch(const Planes& A, const Planes& B, bool split, int bn, const TcGemmArgs& args,
+                               cudaStream_t st) {
+    const int bi = bn_index(bn);
+    const CUtensorMap& alo = split ? A.tm_lo[0] : A.tm_hi[0];
+    const CUtensorMap& blo = split ? B.tm_lo[bi] : B.tm_hi[bi];
+    if (split) {
+      switch (bn) {
+        case 32: return launch_gemm_tc_t<32, true>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+        case 64: return launch_gemm_tc_t<64, true>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+        default: return launch_gemm_tc_t<128, true>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+      }
+    }
+    switch (bn) {
+      case 32: return launch_gemm_tc_t<32, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+      case 64: return launch_gemm_tc_t<64, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+      case 128: return launch_gemm_tc_t<128, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+      default: return launch_gemm_tc_t<256, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+    }
+  }
+
+  cudaError_t gemm(const ActBuf& A, const Linear& L, int M, Epilogue e, cudaStream_t st) {
+    e.bias = L.bias;
+    e.bf16 = bf16();
+    const double flops = 2.0 * M * L.N * L.K;
+    if (!tc()) {
+      Scope sc(this, KC_GEMM_SIMT, flops, 4.0 * (double(M) * L.K + double(L.N) * L.K + double(M) * L.N), st);
+      return launch_gemm_simt(A.f32, A.ld32, L.w32, L.K, M, L.N, L.K, e, st);
+    }
+    const bool split = L.split && A.p.lo != nullptr;
+    const int bn = choose_bn(M, L.N, split);
+    TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, e};
+    const double planes = split ? 2.0 : 1.0;
+    Scope sc(this, KC_GEMM_TC, flops, 2.0 * planes * (double(M) * L.K + double(L.N) * L.K) + 4.0 * double(M) * L.N, st);
+    return gemm_tc_dispatch(A.p, L.p, split, bn, args, st);
+  }
+
+  // destination description shared by LN / attention / GEMM epilogues
+  static void out_to(Epilogue& e, const ActBuf& dst, bool want_f32) {
+    e.out32 = want_f32 ? dst.f32 : nullptr; e.ld32 = dst.ld32;
+    e.out_hi = dst.p.hi; e.out_lo = dst.p.lo; e.ld16 = dst.p.ld;
+  }
+
+  cudaError_t layernorm(const ActBuf& in, int rows, const LNParam& n1, const LNParam* n2, const ActBuf& dst,
+                        bool want_f32, int rows_per_clip, int first_token, cudaStream_t st) {
+    LnArgs a{};
+    a.x = in.f32; a.ldx = in.ld32; a.rows = rows; a.d = cfg.dim_model;
+    a.w1 = n1.w; a.b1 = n1.b; a.w2 = n2 ? n2->w : nullptr; a.b2 = n2 ? n2->b : nullptr;
+    a.eps = cfg.layer_norm_eps;
+    a.rows_per_clip = rows_per_clip; a.first_token = first_token; a.compact = first_token > 0;
+    a.out32 = (want_f32 || !tc()) ? dst.f32 : nullptr; a.ld32 = dst.ld32;
+    a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
+    const double d = cfg.dim_model;
+    Scope sc(this, KC_LN, 0.0, rows * d * (4.0 + (a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0)), st);
+    return launch_layernorm(a, st);
+  }
+
+  cudaError_t attention(const float* q, int ldq, const float* k, const float* v, int ldkv, int B, int Sq, int Sk,
+                        int mask_kind, const float* mask, int q_first, const ActBuf& dst, cudaStream_t st) {
+    AttnArgs a{};
+    a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv;
+    a.clips = B; a.heads = cfg.num_heads; a.hd = cfg.dim_model / cfg.num_heads; a.Sq = Sq; a.Sk = Sk;
+    a.mask_kind = mask_kind; a.mask = mask;
+    a.scale = 1.0f / sqrtf(static_cast<float>(a.hd));
+    a.q_first = q_first;
+    a.out32 = tc() ? nullptr : dst.f32; a.ld32 = dst.ld32;
+    a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
+    const double d = cfg.dim_model;
+    Scope sc(this, KC_ATTN, 0.0,
+             double(B) * d * (4.0 * (Sq + 2.0 * Sk) + Sq * ((a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0))), st);
+    return launch_attention(a, st);
+  }
+
+  cudaError_t pack(const PackArgs& a, cudaStream_t st) {
+    const double n = double(a.clips) * a.tokens * a.width;
+    Scope sc(this, KC_PACK, 0.0, n * (4.0 + (a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0)), st);
+    return launch_pack(a, num_sms, st);
+  }
+
+  // Latents (B, S, E) fp32 (contiguous or gathered from history slots) -> operand buffer `dst`.
+  cudaError_t ingest(const float* src, long long clip_stride, long long slot_stride, const int* slot_list, int B,
+                     int S, float scale, const ActBuf& dst, cudaStream_t st) {
+    PackArgs a{};
+    a.src = src; a.src_clip_stride = clip_stride; a.src_slot_stride = slot_stride;
+    a.clips = B; a.tokens = S; a.width = cfg.latent_dim;
+    for (int t = 0; t < S; ++t) a.slot[t] = slot_list ? slot_list[t] : t;
+    a.fill = 2.0f;  // SOS frame, utils/sd_utils.py:31
+    a.scale = scale;
+    a.out32 = tc() ? nullptr : dst.f32;
+    a.out_clip_stride = static_cast<long long>(S) * dst.ld32; a.out_tok_stride = dst.ld32;
+    a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
+    return pack(a, st);
+  }
+
+#define SDVG_CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return _e; } while (0)
+
+  // One pass of the model on operand buffers lat_s (and lat_t unless `same`).  `oe` describes where the
+  // output latents go (fp32 destination, row mapping).
+  cudaError_t run_model(int B, int Ss, int St, bool same, int mask_kind, const float* mask, const int* pe_index,
+                        Epilogue oe, cudaStream_t st) {
+    const int d = cfg.dim_model;
+    const int Ms = B * Ss, Mt = B * St;
+    const int Le = static_cast<int>(enc.size()), Ld = static_cast<int>(dec.size());
+    const float sqrt_d = sqrtf(static_cast<float>(d));
+
+    auto embed = [&](const ActBuf& lat, int S, const ActBuf& dst) -> cudaError_t {
+      Epilogue e;  // (x W^T + b) * sqrt(d) + PE[pe_index[clip]]   models/transformer.py:53-56
+      e.alpha = sqrt_d; e.pe = pe_table; e.ld_pe = d; e.pe_index = pe_index; e.rows_per_clip = S;
+      out_to(e, dst, true);
+      return gemm(lat, embedding, B * S, e, st);
+    };
+    auto self_attention = [&](const ActBuf& x, const AttnWeights& w, int S, int M, int mk, const float* mptr,
+                              const LNParam& norm, const ActBuf& x_out) -> cudaError_t {
+      Epilogue e;
+      out_to(e, qkv, true); e.out_hi = nullptr; e.out_lo = nullptr;
+      SDVG_CK(gemm(x, w.qkv, M, e, st));
+      SDVG_CK(attention(qkv.f32, 3 * d, qkv.f32 + d, qkv.f32 + 2 * d, 3 * d, B, S, S, mk, mptr, 0, attn, st));
+      Epilogue eo;
+      eo.residual = x.f32; eo.ld_res = x.ld32;
+      out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+      SDVG_CK(gemm(attn, w.out, M, eo, st));
+      return layernorm(ybuf, M, norm, nullptr, x_out, true, S, 0, st);
+    };
+    auto ffn = [&](const ActBuf& x, const Linear& l1, const Linear& l2, int M, int S, const LNParam& norm,
+                   const LNParam* chained, const ActBuf& x_out, bool want_f32) -> cudaError_t {
+      Epilogue e1;
+      e1.relu = 1;
+      out_to(e1, ffh, !tc());
+      SDVG_CK(gemm(x, l1, M, e1, st));
+      Epilogue e2;
+      e2.residual = x.f32; e2.ld_res = x.ld32;
+      out_to(e2, ybuf, true); e2.out_hi = nullptr; e2.out_lo = nullptr;
+      SDVG_CK(gemm(ffh, l2, M, e2, st));
+      return layernorm(ybuf, M, norm, chained, x_out, want_f32, S, 0, st);
+    };
+
+    // ---------------- encoder
+    SDVG_CK(embed(lat_s, Ss, emb_s));
+    const ActBuf* x = &emb_s;
+    for (int l = 0; l < Le; ++l) {
+      SDVG_CK(self_attention(*x, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs));
+      const bool last = (l == Le - 1);
+      SDVG_CK(ffn(xs, enc[l].ff1, enc[l].ff2, Ms, Ss, enc[l].n2, last ? &enc_norm : nullptr, last ? mem : xs, !last));
+      x = &xs;
+    }
+    if (Le == 0) SDVG_CK(layernorm(emb_s, Ms, enc_norm, nullptr, mem, false, Ss, 0, st));
+
+    // ---------------- decoder
+    const ActBuf* y = &emb_s;
+    if (!same) { SDVG_CK(embed(lat_t, St, emb_t)); y = &emb_t; }
+    for (int l = 0; l < Ld; ++l) {
+      SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt));
+      // cross attention: Q from the target stream, K/V from the encoder memory
+      Epilogue eq;
+      out_to(eq, qc, true); eq.out_hi = nullptr; eq.out_lo = nullptr;
+      SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
+      Epilogue ekv;
+      out_to(ekv, kvc, true); ekv.out_hi = nullptr; ekv.out_lo = nullptr;
+      SDVG_CK(gemm(mem, dec[l].ca.kv, Ms, ekv, st));
+      SDVG_CK(attention(qc.f32, d, kvc.f32, kvc.f32 + d, 2 * d, B, St, Ss, 0, nullptr, 0, attn, st));
+      Epilogue eo;
+      eo.residual = xt.f32; eo.ld_res = xt.ld32;
+      out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+      SDVG_CK(gemm(attn, dec[l].ca.out, Mt, eo, st));
+      SDVG_CK(layernorm(ybuf, Mt, dec[l].n2, nullptr, xt, true, St, 0, st));
+      const bool last = (l == Ld - 1);
+      SDVG_CK(ffn(xt, dec[l].ff1, dec[l].ff2, Mt, St, dec[l].n3, last ? &dec_norm : nullptr, last ? fin : xt, !last));
+      y = &xt;
+    }
+    if (Ld == 0) SDVG_CK(layernorm(*y, Mt, dec_norm, nullptr, fin, false, St, 0, st));
+
+    // ---------------- output projection (models/transformer.py:65)
+    oe.rows_per_clip = St; oe.clips = B;
+    return gemm(fin, out_proj, Mt, oe, st);
+  }
+
+  int check_ready(cudaStream_t st) {
+    if (!finalized) { int r = finalize(st); if (r != SDVG_OK) return r; }
+    return SDVG_OK;
+  }
+
+  int forward(const float* src, const float* tgt, int B, int Ss, int St, int mask_kind, const float* mask,
+              const int* pe_index, float* out, cudaStream_t st) {
+    if (!src || !tgt || !out) return fail(SDVG_ERR_INVALID, "null tensor");
+    if (B <= 0 || Ss <= 0 || St <= 0) return fail(SDVG_ERR_INVALID, "empty batch or sequence");
+    if (B > cfg.max_clips || Ss > cfg.max_tokens || St > cfg.max_tokens)
+      return fail(SDVG_ERR_INVALID, "B=%d S_src=%d S_tgt=%d exceed the handle's limits (%d clips, %d tokens)", B, Ss, St, cfg.max_clips, cfg.max_tokens);
+    if (!pe_index && B > 64)
+      return fail(SDVG_ERR_BATCH, "B=%d > 64 without pe_index: the reference's PositionalEncoding (max_len=64, indexed by batch "
+                  "position) raises for this batch (models/transformer.py:33-35, positional_encoding.py:35)", B);
+    if (mask_kind < 0 || mask_kind > 2 || (mask_kind == 2 && !mask)) return fail(SDVG_ERR_INVALID, "bad mask");
+    int r = check_ready(st);
+    if (r != SDVG_OK) return r;
+    const bool same = (src == tgt && Ss == St);
+    const int E = cfg.latent_dim;
+    cudaError_t e = ingest(src, static_cast<long long>(Ss) * E, E, nullptr, B, Ss, 1.0f, lat_s, st);
+    if (e == cudaSuccess && !same) e = ingest(tgt, static_cast<long long>(St) * E, E, nullptr, B, St, 1.0f, lat_t, st);
+    if (e != cudaSuccess) return fail_cuda(e, "ingest");
+    Epilogue oe;
+    oe.out32 = out; oe.ld32 = E; oe.row_map = 1;  // (S_tgt, B, E)
+    e = run_model(B, Ss, St, same, mask_kind, mask, pe_index, oe, st);
+    if (e != cudaSuccess) return fail_cuda(e, "forward");
+    return SDVG_OK;
+  }
+
+  int rollout(const float* ctx, int B, int C, int n_pred, int window, int faithful, const float* teacher,
+              const int* pe_index, float scale_in, float scale_out, float* out, cudaStream_t st) {
+    if (!ctx || !out) return fail(SDVG_ERR_INVALID, "null tensor");
+    if (B <= 0 || C <= 0 || n_pred <= 0 || window <= 0) return fail(SDVG_ERR_INVALID, "empty rollout");
+    if (faithful && C != 5) return fail(SDVG_ERR_INVALID, "faithful mode replays prediction/predict.py, which uses exactly 5 context frames");
+    const int Hn = C + n_pred;
+    const int max_S = faithful ? 6 : (window < Hn ? window : Hn);
+    if (B > cfg.max_clips || Hn > cfg.max_history || max_S > cfg.max_tokens)
+      return fail(SDVG_ERR_INVALID, "rollout B=%d history=%d window=%d exceed the handle's limits (%d clips, %d history, %d tokens)",
+                  B, Hn, max_S, cfg.max_clips, cfg.max_history, cfg.max_tokens);
+    int r = check_ready(st);
+    if (r != SDVG_OK) return r;
+    const int E = cfg.latent_dim;
+    const long long hstride = static_cast<long long>(Hn) * E;
+    const int* pe = pe_index ? pe_index : pe_mod64;
+
+    // context -> history slots [0, C)
+    {
+      PackArgs a{};
+      a.src = ctx; a.src_clip_stride = static_cast<long long>(C) * E; a.src_slot_stride = E;
+      a.clips = B; a.tokens = 1; a.width = C * E; a.slot[0] = 0; a.scale = scale_in;
+      a.out32 = hist; a.out_clip_stride = hstride; a.out_tok_stride = 0;
+      cudaError_t e = pack(a, st);
+      if (e != cudaSuccess) return fail_cuda(e, "context ingest");
+    }
+    std::vector<int> seq;
+    for (int t = 0; t < n_pred; ++t) {
+      seq.clear();
+      if (faithful) {
+        if (t == 0) { seq = {-1, 0, 1, 2, 3, 4}; }             // [SOS, f1..f5]            predict.py:124-130
+        else {                                                  // last 5 of [f1..f4, p1..pt] predict.py:193-196
+          for (int i = 0; i < 4; ++i) seq.push_back(i);
+          for (int k = 0; k < t; ++k) seq.push_back(C + k);
+          if (seq.size() > 5) seq.erase(seq.begin(), seq.end() - 5);
+        }
+      } else {
+        const int have = C + t, W = window < have ? window : have;
+        for (int i = have - W; i < have; ++i) seq.push_back(i);
+      }
+      const int S = static_cast<int>(seq.size());
+      cudaError_t e = ingest(hist, hstride, E, seq.data(), B, S, 1.0f, lat_s, st);
+      if (e != cudaSuccess) return fail_cuda(e, "window gather");
+      Epilogue oe;  // last position of every clip -> history slot C+t          predict.py:42
+      oe.out32 = hist + static_cast<size_t>(C + t) * E; oe.ld32 = static_cast<int>(hstride); oe.row_map = 2;
+      e = run_model(B, S, S, true, 1, nullptr, pe, oe, st);
+      if (e != cudaSuccess) return fail_cuda(e, "rollout step");
+      if (teacher) {
+        // export this prediction, then overwrite the slot with the teacher frame
+        PackArgs x{};
+        x.src = hist + static_cast<size_t>(C + t) * E; x.src_clip_stride = hstride; x.src_slot_stride = 0;
+        x.clips = B; x.tokens = 1; x.width = E; x.slot[0] = 0; x.scale = scale_out;
+        x.out32 = out + static_cast<size_t>(t) * E; x.out_clip_stride = static_cast<long long>(n_pred) * E;
+        if ((e = pack(x, st)) != cudaSuccess) return fail_cuda(e, "export");
+        PackArgs y{};
+        y.src = teacher + static_cast<size_t>(t) * E; y.src_clip_stride = static_cast<long long>(n_pred) * E; y.src_slot_stride = 0;
+        y.clips = B; y.tokens = 1; y.width = E; y.slot[0] = 0; y.scale = 1.0f;
+        y.out32 = hist + static_cast<size_t>(C + t) * E; y.out_clip_stride = hstride;
+        if ((e = pack(y, st)) != cudaSuccess) return fail_cuda(e, "teacher ingest");
+      }
+    }
+    if (!teacher) {
+      PackArgs x{};
+      x.src = hist + static_cast<size_t>(C) * E; x.src_clip_stride = hstride; x.src_slot_stride = 0;
+      x.clips = B; x.tokens = 1; x.width = n_pred * E; x.slot[0] = 0; x.scale = scale_out;
+      x.out32 = out; x.out_clip_stride = static_cast<long long>(n_pred) * E;
+      cudaError_t e = pack(x, st);
+      if (e != cudaSuccess) return fail_cuda(e, "export");
+    }
+    return SDVG_OK;
+  }
+};
+
+}  // namespace sdvg

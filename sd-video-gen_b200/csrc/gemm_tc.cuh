@@ -1,0 +1,278 @@
+// K1 - tensor-core GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T, then the fused Epilogue (common.cuh).
+//
+// Replaces every nn.Linear / packed in-proj of the reference path (models/transformer.py:37,45 and the
+// torch.nn.Transformer layers built at :38-44): embed, QKV, cross-Q/KV, out-proj, FF1, FF2, out.
+//
+// Design (one CTA = one SM, persistent over output tiles, 192 threads):
+//   warp 0 : TMA producer   - cp.async.bulk.tensor 2-D loads of the A (activation) and W (weight) K-slabs
+//                             (64 x 16-bit = 128-byte rows, SWIZZLE_128B) into a multi-stage smem ring
+//   warp 1 : MMA issuer     - one lane issues tcgen05.mma kind::f16 (M=128, N=BN, K=16) with fp32
+//                             accumulators in TMEM; tcgen05.commit releases smem stages / publishes tiles
+//   warps 2-5 : epilogue    - tcgen05.ld (32 lanes x 32 columns per warp), transpose through padded smem so
+//                             global traffic is row-contiguous, bias / scale / PE / ReLU / residual, stores of
+//                             the fp32 result and/or the 16-bit operand planes of the next GEMM
+//   TMEM accumulators are double-buffered: the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Both operands are K-major (PyTorch weights are [N][K], so x W^T needs no transpose).
+//
+// SPLIT = true is the fp32-parity mode: A and W each come as two fp16 planes (x = hi + 2^-11 lo) and three
+// products are accumulated - hi*hi into accumulator 0, hi*lo + lo*hi into accumulator 1 (kept scaled by 2^11,
+// so nothing underflows) - and combined in the epilogue.  22 significant bits per operand at 3 MMAs.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sdvg {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 64;
+constexpr int kTcThreads = 192;
+constexpr int kTcEpiStride = 33;  // floats; 32x32 transpose tile, padded
+constexpr int kTcSmemLimit = 232448;  // 227 KB
+
+template <int BN, bool SPLIT>
+struct TcCfg {
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+  static_assert(!(SPLIT && BN == 256), "split mode needs two accumulators per tile: BN <= 128");
+  static constexpr int kPlanes = SPLIT ? 2 : 1;
+  static constexpr int kABytes = kTcBM * kTcBK * 2;
+  static constexpr int kBBytes = BN * kTcBK * 2;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kEpiBytes = 4 * 32 * kTcEpiStride * 4;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kMaxStages = (kTcSmemLimit - 1024 /*align slack*/ - kEpiBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kColsPerTile = BN * kPlanes;
+  static constexpr int kTmemCols = (2 * kColsPerTile) < 32 ? 32 : (2 * kColsPerTile);
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + kBarBytes;
+  static_assert(kStages >= 2, "pipeline depth");
+  static_assert(kTmemCols <= 512, "TMEM");
+};
+
+struct TcGemmArgs {
+  int M, N, K;
+  int bf16;  // operand format of the hi planes
+  Epilogue epi;
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ TcGemmArgs args) {
+  using Cfg = TcCfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* epi_stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
+  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int M = args.M, N = args.N, K = args.K;
+  const int m_tiles = (M + kTcBM - 1) / kTcBM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kTcBK - 1) / kTcBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull_bar[b], 1);
+      ptx::mbar_init(&tempty_bar[b], 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmA_hi);
+    ptx::prefetch_tensormap(&tmB_hi);
+    if (SPLIT) {
+      ptx::prefetch_tensormap(&tmA_lo);
+      ptx::prefetch_tensormap(&tmB_lo);
+    }
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          ptx::tma_load_2d(sp, &tmA_hi, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
+          if (SPLIT) ptx::tma_load_2d(sp + Cfg::kABytes, &tmA_lo, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
+          uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
+          ptx::tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kTcBK, n_blk * BN);
+          if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &tmB_lo, &full_bar[stage], kb * kTcBK, n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(kTcBM, BN, args.bf16 != 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t buf_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
+        const uint32_t d1 = d0 + BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
+          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
+          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(sb);
+          const uint64_t a_lo = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
+          const uint64_t b_lo = ptx::make_kmajor_sw128_desc(sb + Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kTcBK / 16; ++k) {
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B = 2 << 4
+            ptx::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
+            if (SPLIT) {
+              ptx::umma_f16(d1, a_hi + adv, b_lo + adv, idesc, acc);
+              ptx::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[buf]);  // accumulator(s) of this tile complete
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (4 x 32 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
+    float* stg = epi_stage + q * 32 * kTcEpiStride;
+    const Epilogue& e = args.epi;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
+      ptx::mbar_wait(&tfull_bar[buf], buf_phase);
+      ptx::tc_fence_after();
+      const int row0 = m_blk * kTcBM + q * 32;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
+        if (SPLIT) {
+          uint32_t r1[32];
+          ptx::tmem_ld_32x32b_x32(tbase + BN + c * 32, r1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            stg[lane * kTcEpiStride + i] = fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i]));
+        } else {
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[lane * kTcEpiStride + i] = __uint_as_float(r0[i]);
+        }
+        if (c == BN / 32 - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator back before the global stores
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+        } else {
+          __syncwarp();
+        }
+        const int col = n_blk * BN + c * 32 + lane;
+        if (col < N) {
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int row = row0 + r;
+            if (row >= M) break;
+            const float v = epi_value(e, stg[r * kTcEpiStride + lane], row, col, epi_pe_row(e, row));
+            epi_store(e, v, row, epi_out_row(e, row), col);
+          }
+        }
+        __syncwarp();
+      }
+      if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D map over a row-major 16-bit matrix [rows][cols] (cols contiguous, row pitch ld elements):
+// box = 64 columns (128 B, one swizzle span) x box_rows rows.
+inline bool make_tmap_2d(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows, bool bf16) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kTcBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool SPLIT>
+inline cudaError_t launch_gemm_tc_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                                    const CUtensorMap& b_lo, const TcGemmArgs& args, int num_sms,
+                                    cudaStream_t stream) {
+  using Cfg = TcCfg<BN, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = ceil_div(args.M, kTcBM) * ceil_div(args.N, BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tc_kernel<BN, SPLIT><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, args);
+  return cudaGetLastError();
+}
+
+}  // namespace sdvg

@@ -1,0 +1,114 @@
+// K3 - LayerNorm over the model width (post-norm layers of torch.nn.Transformer, eps 1e-5, biased variance),
+// optionally chained with a second LayerNorm (last encoder layer: norm2 -> encoder.norm; last decoder layer:
+// norm3 -> decoder.norm).  The residual add already happened in the producing GEMM's epilogue.
+// One warp per token row held entirely in registers (two-pass mean / variance), 128-bit loads and stores;
+// emits the fp32 residual stream and/or the 16-bit operand planes of the next GEMM.  HBM/L2-bound:
+// 4 d bytes in, (4 + 2..4) d bytes out per row.
+#pragma once
+#include "common.cuh"
+
+namespace sdvg {
+
+struct LnArgs {
+  const float* x; int ldx;
+  int rows, d;
+  const float* w1; const float* b1;
+  const float* w2; const float* b2;  // nullptr: single LayerNorm
+  float eps;
+  // only rows with (row % rows_per_clip) >= first_token are processed; outputs are compacted to
+  // (clip, token - first_token) rows when compact != 0 (last-token pruning of the final decoder layer)
+  int rows_per_clip, first_token, compact;
+  float* out32; int ld32;
+  uint16_t* out_hi; uint16_t* out_lo; int ld16; int bf16;
+};
+
+template <int NV>
+__device__ __forceinline__ void ln_inplace(float4 (&v)[NV], int d, int lane, const float* __restrict__ w,
+                                           const float* __restrict__ b, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if ((i * 32 + lane) * 4 < d) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if ((i * 32 + lane) * 4 < d) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(d) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+      v[i].x = (v[i].x - mean) * rstd * ww.x + bb.x;
+      v[i].y = (v[i].y - mean) * rstd * ww.y + bb.y;
+      v[i].z = (v[i].z - mean) * rstd * ww.z + bb.z;
+      v[i].w = (v[i].w - mean) * rstd * ww.w + bb.w;
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_kernel(const __grid_constant__ LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);  // index among processed rows
+  const int keep = a.rows_per_clip - a.first_token;
+  const int clips = a.rows / a.rows_per_clip;
+  if (r >= clips * keep) return;
+  const int clip = r / keep, tok = a.first_token + (r - clip * keep);
+  const size_t in_row = static_cast<size_t>(clip) * a.rows_per_clip + tok;
+  const size_t out_row = a.compact ? static_cast<size_t>(r) : in_row;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    v[i] = c < a.d ? *reinterpret_cast<const float4*>(a.x + in_row * a.ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  ln_inplace<NV>(v, a.d, lane, a.w1, a.b1, a.eps);
+  if (a.w2) ln_inplace<NV>(v, a.d, lane, a.w2, a.b2, a.eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c >= a.d) continue;
+    if (a.out32) *reinterpret_cast<float4*>(a.out32 + out_row * a.ld32 + c) = v[i];
+    if (a.out_hi) {
+      const float f[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint16_t hi[4], lo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { hi[t] = to_plane_hi(f[t], a.bf16); lo[t] = to_plane_lo(f[t], hi[t]); }
+      *reinterpret_cast<uint2*>(a.out_hi + out_row * a.ld16 + c) =
+          make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+      if (a.out_lo)
+        *reinterpret_cast<uint2*>(a.out_lo + out_row * a.ld16 + c) =
+            make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+    }
+  }
+}
+
+inline cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream) {
+  if (a.d % 4 != 0 || a.d > 4096) return cudaErrorInvalidValue;
+  const int keep = a.rows_per_clip - a.first_token;
+  const int nrows = (a.rows / a.rows_per_clip) * keep;
+  const int grid = ceil_div(nrows, 4);
+  if (grid == 0) return cudaSuccess;
+  const int nv = ceil_div(a.d, 128);
+  if (nv <= 1) layernorm_kernel<1><<<grid, 128, 0, stream>>>(a);
+  else if (nv <= 2) layernorm_kernel<2><<<grid, 128, 0, stream>>>(a);
+  else if (nv <= 4) layernorm_kernel<4><<<grid, 128, 0, stream>>>(a);
+  else if (nv <= 8) layernorm_kernel<8><<<grid, 128, 0, stream>>>(a);
+  else if (nv <= 16) layernorm_kernel<16><<<grid, 128, 0, stream>>>(a);
+  else layernorm_kernel<32><<<grid, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace sdvg

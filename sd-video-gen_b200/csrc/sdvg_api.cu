@@ -1,0 +1,191 @@
+// C ABI of libsdvg.so (declared in include/sdvg.h).  Thin, exception-free shims over sdvg::Engine.
+#include <new>
+
+#include "engine.cuh"
+
+using sdvg::Engine;
+
+struct sdvg_handle {
+  Engine eng;
+};
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int sdvg_version(void) { return SDVG_VERSION; }
+
+const char* sdvg_last_error(const sdvg_handle* h) { return h ? h->eng.err.c_str() : g_create_error.c_str(); }
+
+int sdvg_create(const sdvg_config* cfg, sdvg_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return SDVG_ERR_INVALID; }
+  *out = nullptr;
+  sdvg_handle* h = new (std::nothrow) sdvg_handle();
+  if (!h) { g_create_error = "out of host memory"; return SDVG_ERR_INVALID; }
+  int r;
+  try {
+    r = h->eng.init(*cfg);
+  } catch (const std::exception& ex) {
+    h->eng.err = std::string("exception: ") + ex.what();
+    r = SDVG_ERR_INVALID;
+  }
+  if (r != SDVG_OK) {
+    g_create_error = h->eng.err;
+    delete h;
+    return r;
+  }
+  *out = h;
+  return SDVG_OK;
+}
+
+void sdvg_destroy(sdvg_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->eng.cfg.device);
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+int sdvg_workspace_bytes(const sdvg_handle* h, size_t* bytes) {
+  if (!h || !bytes) return SDVG_ERR_INVALID;
+  *bytes = h->eng.bytes_owned;
+  return SDVG_OK;
+}
+
+int sdvg_set_weight(sdvg_handle* h, const char* key, const void* data, const int64_t* shape, int32_t ndim) {
+  if (!h) return SDVG_ERR_INVALID;
+  if (!data || !shape) return h->eng.fail(SDVG_ERR_INVALID, "null argument");
+  cudaSetDevice(h->eng.cfg.device);
+  return h->eng.set_weight(key, data, shape, ndim);
+}
+
+int sdvg_num_weights(const sdvg_handle* h) { return h ? static_cast<int>(h->eng.slots.size()) : SDVG_ERR_INVALID; }
+
+const char* sdvg_weight_key(const sdvg_handle* h, int32_t i) {
+  if (!h || i < 0 || i >= static_cast<int>(h->eng.slots.size())) return nullptr;
+  return h->eng.slots[i].key.c_str();
+}
+
+int sdvg_finalize_weights(sdvg_handle* h, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  return h->eng.finalize(static_cast<cudaStream_t>(stream));
+}
+
+int sdvg_forward(sdvg_handle* h, const float* src, const float* tgt, int32_t B, int32_t S_src, int32_t S_tgt,
+                 int32_t mask_kind, const float* mask, const int32_t* pe_index, float* out, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  return h->eng.forward(src, tgt, B, S_src, S_tgt, mask_kind, mask, pe_index, out, static_cast<cudaStream_t>(stream));
+}
+
+int sdvg_rollout(sdvg_handle* h, const float* ctx, int32_t B, int32_t C, int32_t n_pred, int32_t window,
+                 int32_t faithful, const float* teacher, const int32_t* pe_index, float scale_in, float scale_out,
+                 float* out, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  return h->eng.rollout(ctx, B, C, n_pred, window, faithful, teacher, pe_index, scale_in, scale_out, out,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int sdvg_timing_enable(sdvg_handle* h, int32_t on) {
+  if (!h) return SDVG_ERR_INVALID;
+  h->eng.timing = on != 0;
+  return SDVG_OK;
+}
+
+int sdvg_timing_read(sdvg_handle* h, double* ms, int64_t* launches, double* flops, double* bytes) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  return h->eng.timing_read(ms, launches, flops, bytes);
+}
+
+int64_t sdvg_launch_count(const sdvg_handle* h) { return h ? h->eng.launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W, const float* bias, int32_t relu,
+              float* C, int32_t M, int32_t N, int32_t K, int32_t block_n, int32_t iters, float* ms, void* stream) {
+  using namespace sdvg;
+  if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0) { g_create_error = "sdvg_gemm: bad argument"; return SDVG_ERR_INVALID; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "sdvg_gemm: no such CUDA device"; return SDVG_ERR_CUDA; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (iters < 1) iters = 1;
+  Epilogue e;
+  e.bias = bias; e.relu = relu; e.out32 = C; e.ld32 = N;
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+  cudaError_t err = cudaSuccess;
+  int rc = SDVG_OK;
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); cudaEventDestroy(ev0); cudaEventDestroy(ev1); };
+  if (precision == SDVG_FP32_SIMT) {
+    cudaEventRecord(ev0, st);
+    for (int i = 0; i < iters && err == cudaSuccess; ++i) err = launch_gemm_simt(A, K, W, K, M, N, K, e, st);
+    cudaEventRecord(ev1, st);
+  } else {
+    const bool split = precision == SDVG_FP32, bf = precision == SDVG_BF16;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10 || !get_encode_fn()) { cleanup(); g_create_error = "sdvg_gemm: needs an sm_100 device"; return SDVG_ERR_CUDA; }
+    const int Kp = round_up(K, kTcBK), Mp = round_up(M, kTcBM);
+    uint16_t *a_hi = nullptr, *a_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
+    auto alloc16 = [&](uint16_t** p, size_t n) {
+      if (cudaMalloc(reinterpret_cast<void**>(p), n * 2) != cudaSuccess) return false;
+      tmp.push_back(*p);
+      return cudaMemsetAsync(*p, 0, n * 2, st) == cudaSuccess;
+    };
+    bool ok = alloc16(&a_hi, size_t(Mp) * Kp) && alloc16(&w_hi, size_t(N) * Kp);
+    if (ok && split) ok = alloc16(&a_lo, size_t(Mp) * Kp) && alloc16(&w_lo, size_t(N) * Kp);
+    if (!ok) { cleanup(); g_create_error = "sdvg_gemm: out of device memory"; return SDVG_ERR_CUDA; }
+    auto pack16 = [&](const float* src, int rows, uint16_t* hi, uint16_t* lo) {
+      PackArgs a{};
+      a.src = src; a.src_clip_stride = K; a.clips = rows; a.tokens = 1; a.width = K; a.slot[0] = 0; a.scale = 1.f;
+      a.out_hi = hi; a.out_lo = lo; a.ld16 = Kp; a.bf16 = bf;
+      return launch_pack(a, prop.multiProcessorCount, st);
+    };
+    err = pack16(A, M, a_hi, a_lo);
+    if (err == cudaSuccess) err = pack16(W, N, w_hi, w_lo);
+    int bn = block_n;
+    if (bn == 0) {
+      Engine tmp_eng; tmp_eng.num_sms = prop.multiProcessorCount;
+      bn = tmp_eng.choose_bn(M, N, split);
+    }
+    if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256) || (split && bn == 256) || (bn > N && bn > 32)) {
+      cleanup(); g_create_error = "sdvg_gemm: bad block_n"; return SDVG_ERR_INVALID;
+    }
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const int boxn = bn > N ? N : bn;
+    ok = make_tmap_2d(&ta_hi, a_hi, Mp, Kp, Kp, kTcBM, bf) && make_tmap_2d(&tb_hi, w_hi, N, Kp, Kp, boxn, bf);
+    if (ok && split) ok = make_tmap_2d(&ta_lo, a_lo, Mp, Kp, Kp, kTcBM, false) && make_tmap_2d(&tb_lo, w_lo, N, Kp, Kp, boxn, false);
+    if (!ok) { cleanup(); g_create_error = "sdvg_gemm: cuTensorMapEncodeTiled failed"; return SDVG_ERR_CUDA; }
+    if (!split) { ta_lo = ta_hi; tb_lo = tb_hi; }
+    TcGemmArgs args{M, N, K, bf ? 1 : 0, e};
+    const int sms = prop.multiProcessorCount;
+    cudaEventRecord(ev0, st);
+    for (int i = 0; i < iters && err == cudaSuccess; ++i) {
+      if (split) {
+        if (bn == 32) err = launch_gemm_tc_t<32, true>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+        else if (bn == 64) err = launch_gemm_tc_t<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+        else err = launch_gemm_tc_t<128, true>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+      } else {
+        if (bn == 32) err = launch_gemm_tc_t<32, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+        else if (bn == 64) err = launch_gemm_tc_t<64, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+        else if (bn == 128) err = launch_gemm_tc_t<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+        else err = launch_gemm_tc_t<256, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
+      }
+    }
+    cudaEventRecord(ev1, st);
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) {
+    g_create_error = std::string("sdvg_gemm: ") + cudaGetErrorString(err);
+    rc = SDVG_ERR_CUDA;
+  } else if (ms) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ev0, ev1);
+    *ms = t / iters;
+  }
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+"""CPU: host-side mirror of the reference interface (module contract, state_dict, masks, sharding)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import sdvg_b200
+from conftest import ROOT, load_golden, ref_model_from_golden
+from oracle import rollout as R
+from oracle.ref_module import RefTransformer
+
+
+def test_state_dict_matches_reference_keys_and_init():
+    g = load_golden("tiny_forward")
+    ref_keys = sorted(k[3:] for k in g if k.startswith("sd."))
+    torch.manual_seed(0)
+    ours = sdvg_b200.Transformer(0, 32, 4, 1, 1, 0.1, frame_size=64)
+    sd = ours.state_dict()
+    assert sorted(sd) == ref_keys
+    for k in ref_keys:
+        assert tuple(sd[k].shape) == tuple(g["sd." + k].shape), k
+        # same construction order as the reference -> identical seeded init
+        assert torch.equal(sd[k], g["sd." + k]), k
+    ours.load_state_dict({k: g["sd." + k] for k in ref_keys})          # reference checkpoints load
+
+
+def test_default_ctor_shapes_like_reference():
+    m = sdvg_b200.Transformer(frame_size=64)                            # Transformer() defaults, models/transformer.py:14-19
+    assert m.dim_model == 256 and m.height == 64 and m.width == 64 and m.compression == 8
+    assert len(m.transformer.encoder.layers) == 6 and len(m.transformer.decoder.layers) == 6
+    assert m.embedding.in_features == 256 and m.out.out_features == 256
+    assert m.transformer.encoder.layers[0].linear1.out_features == 2048
+    assert tuple(m.positional_encoder.pos_encoding.shape) == (64, 1, 256)
+
+
+def test_ctor_reads_frame_size_from_argv_and_yaml(tmp_path, monkeypatch):
+    """models/transformer.py:23,28-29: without frame_size the ctor parses --dataset/--config and ./config/<name>.yml."""
+    (tmp_path / "config").mkdir()
+    (tmp_path / "config" / "demo.yml").write_text("FRAME_SIZE: 128\nDIM_MODEL:\n - 64\n")
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["x", "--dataset", "ball", "--config", "demo"])
+    m = sdvg_b200.Transformer(0, 32, 4, 1, 1, 0.1)
+    assert m.height == 128 and m.embedding.in_features == 1024 and m.config.CONFIG_NAME == "demo"
+    monkeypatch.setattr(sys, "argv", ["x"])
+    with pytest.raises(SystemExit):                                      # argparse: required flags, like the reference
+        sdvg_b200.Transformer(0, 32, 4, 1, 1, 0.1)
+
+
+def test_masks_match_reference():
+    m = sdvg_b200.Transformer(0, 32, 4, 1, 1, 0.1, frame_size=64)
+    r = RefTransformer(0, 32, 4, 1, 1, 0.1, frame_size=64)
+    for s in (1, 2, 5, 6, 10):
+        assert torch.equal(m.get_tgt_mask(s), r.get_tgt_mask(s))
+    x = torch.tensor([1, 2, 3, 0, 0, 0])
+    assert torch.equal(m.create_pad_mask(x, 0), r.create_pad_mask(x, 0))
+
+
+def test_b65_raises_before_any_device_work():
+    m = sdvg_b200.Transformer(0, 32, 4, 1, 1, 0.1, frame_size=64).eval()
+    x = torch.zeros(65, 2, 256)
+    with pytest.raises(RuntimeError, match=r"size of tensor a \(65\)"):
+        m(x, x)
+    with pytest.raises(RuntimeError, match="padding masks"):
+        m(x[:2], x[:2], None, torch.zeros(2, 2, dtype=torch.bool))
+    m.train()
+    with pytest.raises(RuntimeError, match="inference path"):
+        m(x[:2], x[:2])
+
+
+def test_configs_table():
+    c = sdvg_b200.CONFIGS
+    assert c["1_17_ball_complex_L1_64"]["dim_model"] == 2048 and c["1_17_ball_complex_L1_64"]["num_decoder_layers"] == 8
+    assert c["11_20_wallpushups_dim_2048"]["num_encoder_layers"] == 6
+    assert sdvg_b200.latent_dim(64) == 256 and sdvg_b200.latent_dim(128) == 1024
+
+
+def test_shard_bounds_cover_and_align():
+    for B in (1, 8, 63, 64, 65, 128, 1000, 1024, 8192):
+        for W in (1, 2, 3, 4, 8):
+            spans = [sdvg_b200.shard_bounds(B, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            for a, b in spans:
+                assert a % 64 == 0 or a == B
+    assert sdvg_b200.pe_index_for(60, 70).tolist() == [60, 61, 62, 63, 0, 1, 2, 3, 4, 5]
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    g = load_golden("small_rollout")
+    model = ref_model_from_golden(g)
+    sd = model.state_dict()
+    ctx = torch.randn(130, 6, 256, generator=torch.Generator().manual_seed(5))    # > 2 chunks of 64, ragged tail
+
+    def oracle_rollout(c, n_pred, window, pe_index=None):
+        from oracle import functional as F
+
+        class M:
+            get_tgt_mask = staticmethod(F.causal_mask)
+
+            def __call__(self, s, t, mask):
+                return F.forward(sd, s, t, 8, mask, pe_index=pe_index.long())
+        return R.rollout_ref(M(), c, n_pred, window)
+
+    with torch.no_grad():
+        got = sdvg_b200.rollout_sharded(oracle_rollout, ctx, 2, 5, rank=rank, world_size=world)
+        if rank == 0:
+            want = R.chunked(lambda c: R.rollout_ref(model, c, 2, 5), ctx)          # the reference in chunks of 64
+            torch.save((got, want), tmp)
+    dist.destroy_process_group()
+
+
+def test_sharded_rollout_equals_chunked_reference_gloo(tmp_path):
+    """world_size-2 gloo: shards keep PE[i mod 64], gather restores clip order; equals the reference run in
+    chunks of <= 64 clips."""
+    tmp = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, 29541, tmp), nprocs=2, join=True)
+    got, want = torch.load(tmp)
+    assert got.shape == want.shape == (130, 2, 256)
+    assert R.max_rel_per_frame(got, want).max() < 5e-5
