@@ -1,0 +1,309 @@
+"""bench.py - latent frames/sec of the autoregressive rollout (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm (libsdvg, sm_100a kernels)
+    python bench.py --impl reference [...]                      # reference arm: the reference's CPU path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...       # N > 1: one rank per GPU, clips sharded
+
+A "step" is one full rollout of the workload: B clips x n_pred predicted latent frames (n_pred transformer
+passes, prediction/predict.py:143-197).  Default workload = BASELINE.json configs[1]: the KITTI 64x64 model
+(1_15_kitti_L1_64: d2048 H8 4enc/8dec, E=256), B=1024 clips per GPU, 10 context -> 10 predicted frames, window 5
+(the reference's hard-coded window, predict.py:196), synthetic N(0,1) latents, seeded random-init weights.
+Weak scaling: every GPU rolls out its own 1024 clips (clip i uses PE row i mod 64 like the reference run in
+64-clip chunks); the predictions are all-gathered inside the timed step.
+
+value   : whole-job latent frames/s with the context already resident in HBM.
+e2e     : same through host buffers (pinned H2D of the context and D2H of the predictions inside the timed region).
+roofline: tensor-core GEMM kernel class (the dominant kernel): algorithmic 2MNK FLOPs / CUDA-event time of those
+          launches, measured live in an instrumented pass of the same workload, against MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: the oracle port of the reference path (oracle/ref_module.py on torch CPU, i.e.
+          the reference's own nn.Transformer arithmetic) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "latent_frames_per_sec_rollout"
+UNIT = "latent frames/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="1_15_kitti_L1_64")
+    p.add_argument("--batch", type=int, default=1024, help="clips per GPU")
+    p.add_argument("--context", type=int, default=10)
+    p.add_argument("--pred", type=int, default=10)
+    p.add_argument("--window", type=int, default=5)
+    p.add_argument("--precision", default="fp16", choices=["fp32_simt", "fp32", "fp16", "bf16", "mixed"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample-steps", type=int, default=2)
+    return p.parse_args()
+
+
+def flops_per_clip_step(cfg, E, W):
+    """Reference full-window forward GEMM FLOPs per clip-step, embedding counted once when src==tgt
+    is NOT assumed here: this is the reference's work (F_ref)."""
+    d, ff, Le, Ld = cfg["dim_model"], 2048, cfg["num_encoder_layers"], cfg["num_decoder_layers"]
+    return W * Le * (8 * d * d + 4 * d * ff) + W * Ld * (16 * d * d + 4 * d * ff) + 2 * W * 2 * E * d + W * 2 * d * E
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
+        # samples taken under load = upper half of the distribution is not needed: median of all in-region samples
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows and len(self.rows[0]) > 1 else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if len(r) > 2), default=None),
+                "samples": len(sm), "reasons": reasons}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=p.get("bf16_tflops_sustained", p.get("bf16_tflops")), burst=p.get("bf16_tflops"),
+                    hbm=p.get("hbm_gbs"), source="measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_setup(cfg, seed=0):
+    import torch
+    from oracle.ref_module import RefTransformer
+    torch.manual_seed(seed)
+    m = RefTransformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"],
+                       cfg["dropout_p"], frame_size=cfg["frame_size"]).eval()
+    return m
+
+
+def cpu_reference_step(model, ctx, n_pred, window):
+    """One bounded sample: the reference's path on <= 64 clips (its batch limit), n_pred rollout steps."""
+    import torch
+    from oracle import rollout as R
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        out = R.rollout_ref(model, ctx, n_pred, window)
+        dt = time.perf_counter() - t0
+    return out, dt
+
+
+def run_reference_arm(a, cfg, E):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = cpu_reference_setup(cfg)
+    clips, n_pred = 64, a.cpu_sample_steps
+    ctx = torch.randn(clips, a.context, E, generator=torch.Generator().manual_seed(1234))
+    for _ in range(max(1, min(a.warmup, 2))):
+        cpu_reference_step(model, ctx[:8], 1, a.window)
+    times = []
+    for _ in range(a.steps):
+        _, dt = cpu_reference_step(model, ctx, n_pred, a.window)
+        times.append(dt)
+    T = sum(times) / len(times)
+    value = clips * n_pred / T
+    sample = (f"per step: one 64-clip chunk (the reference's batch limit) x {n_pred} rollout steps of the same "
+              f"model/window; {a.steps} steps timed; threads={torch.get_num_threads()}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.config} rollout, {a.context} ctx -> {a.pred} pred, window {a.window}",
+                   "arch": cfg, "sample_clips": clips, "sample_pred": n_pred},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(a, cfg, E):
+    import torch
+    import torch.distributed as dist
+    import sdvg_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libsdvg has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, C, P, W = a.batch, a.context, a.pred, a.window
+
+    torch.manual_seed(0)   # same weights on every rank
+    model = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"],
+                                  cfg["num_decoder_layers"], cfg["dropout_p"], frame_size=cfg["frame_size"],
+                                  precision=a.precision, max_clips=B, max_tokens=min(W, C + P), max_history=C + P)
+    model = model.eval().to(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    ctx_host = torch.randn(B, C, E, generator=g)
+    ctx = ctx_host.to(dev)
+    pe = sdvg_b200.pe_index_for(rank * B, (rank + 1) * B, dev)
+    out = torch.empty(B, P, E, device=dev)
+    gathered = torch.empty(world * B, P, E, device=dev) if world > 1 else None
+
+    def step():
+        sdvg_b200.rollout(model, ctx, P, W, pe_index=pe, out=out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = model.launch_count()
+    ms = timed(step, a.steps)
+    launches = model.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    frames = world * B * P * a.steps
+    value = frames / (ms / 1e3)
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region
+    host = sdvg_b200.HostRollout(model, B, C, P, dev)
+    host.ctx_pinned.copy_(ctx_host)
+
+    def step_e2e():
+        host(None, W, pe_index=pe)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    e2e = {"value": frames / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes * world,
+           "d2h_bytes_per_step": host.d2h_bytes * world, "ms_per_step": ms_e2e / a.steps}
+
+    # ---- roofline of the dominant kernel class: instrumented pass (CUDA events around every launch)
+    model.timing(True)
+    model.timing_read()
+    step()
+    prof = model.timing_read()
+    model.timing(False)
+    pk = peaks()
+    cls = "gemm_tc" if prof["gemm_tc"]["launches"] else "gemm_simt"
+    gk = prof[cls]
+    achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12 if gk["ms"] > 0 else 0.0
+    total_ms = sum(v["ms"] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": f"sdvg::gemm_tc_kernel ({cls})", "achieved": achieved, "peak": pk["tflops"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                "launches_per_step": gk["launches"], "avg_launch_us": gk["ms"] * 1e3 / max(1, gk["launches"]),
+                "share_of_step": gk["ms"] / total_ms if total_ms else None,
+                "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+                "classes_gbs": {k: (round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None)
+                                for k, v in prof.items() if k in ("attention", "layernorm", "pack")},
+                "hbm_peak_gbs": pk["hbm"]}
+    # whole-step view: reference-equivalent FLOPs (F_ref) over the device-timed step
+    f_ref = flops_per_clip_step(cfg, E, min(W, C)) * B * P
+    roofline["step_tflops_ref_equiv"] = f_ref / (ms / a.steps * 1e-3) / 1e12
+    roofline["step_frac_of_peak"] = roofline["step_tflops_ref_equiv"] / pk["tflops"]
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "fp16 operands, fp32 accumulate", "bf16": "bf16 operands, fp32 accumulate",
+                      "fp32": "fp32 (split fp16x2 operands on tensor cores, fp32 accumulate)",
+                      "fp32_simt": "fp32", "mixed": "fp16 + split first layers, fp32 accumulate"}[a.precision],
+            "data": "synthetic",
+            "config": {"workload": f"{a.config} rollout: {B} clips/GPU x {world} GPU, {C} ctx -> {P} pred, window {W}",
+                       "arch": cfg, "precision": a.precision, "clips_per_gpu": B, "global_clips": B * world,
+                       "parallelism": f"dp{world} (clip-sharded, final all-gather)",
+                       "l2": "no flush: per-step working set (>=0.9 GB weights + activations) exceeds the 126 MB L2"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            import torch as _t
+            cores = os.cpu_count() or 1
+            _t.set_num_threads(cores)
+            cpu_model = cpu_reference_setup(cfg)
+            cctx = ctx_host[:64]
+            cpu_reference_step(cpu_model, cctx[:8], 1, W)
+            out_cpu, dt = cpu_reference_step(cpu_model, cctx, a.cpu_sample_steps, W)
+            line["cpu_baseline"] = {
+                "value": 64 * a.cpu_sample_steps / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                "sample": f"first 64 clips (the reference's batch limit) x {a.cpu_sample_steps} rollout steps of the same "
+                          f"workload, {dt:.1f} s of CPU time; oracle/ref_module.py (torch.nn.Transformer, fp32)"}
+            # free parity read-out on the sample (teacher-free first frames)
+            from oracle import rollout as R
+            err = R.max_rel_per_frame(out[:64, :a.cpu_sample_steps].cpu(), out_cpu)
+            line["parity_vs_cpu_sample"] = [float(e) for e in err]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    import sdvg_b200
+    cfg = {k: v for k, v in sdvg_b200.CONFIGS[a.config].items()}
+    E = sdvg_b200.latent_dim(cfg["frame_size"])
+    if a.impl == "reference":
+        run_reference_arm(a, cfg, E)
+    else:
+        run_ours(a, cfg, E)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,7 @@ namespace sdvg {
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;
 constexpr int kTcThreads = 192;
-constexpr int kTcEpiStride = 33;  // floats; 32x32 transpose tile, padded
+constexpr int kTcEpiStride = 36;  // floats; 32x32 transpose tile, padded to keep 128-bit accesses conflict-free
 constexpr int kTcSmemLimit = 232448;  // 227 KB
 
 template <int BN, bool SPLIT>
@@ -52,6 +52,7 @@ struct TcCfg {
 struct TcGemmArgs {
   int M, N, K;
   int bf16;  // operand format of the hi planes
+  int vec4;  // all epilogue pointers / pitches are 16-byte aligned and N % 4 == 0 (set by the launcher)
   Epilogue epi;
 };
 
@@ -170,6 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
     float* stg = epi_stage + q * 32 * kTcEpiStride;
     const Epilogue& e = args.epi;
+    // transposed read-back: 8 lanes x float4 cover the 32 columns of one row, 4 rows per pass, 8 passes
+    const int lr = lane >> 3, lc = (lane & 7) * 4;
     int buf = 0;
     uint32_t buf_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -187,13 +190,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           ptx::tmem_ld_32x32b_x32(tbase + BN + c * 32, r1);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            stg[lane * kTcEpiStride + i] = fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i]));
+          for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i])));
         } else {
           ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) stg[lane * kTcEpiStride + i] = __uint_as_float(r0[i]);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(&stg[lane * kTcEpiStride + 4 * j]) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
         if (c == BN / 32 - 1) {
           // all TMEM reads of this tile are done: hand the accumulator back before the global stores
           ptx::tc_fence_before();
@@ -202,14 +205,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         } else {
           __syncwarp();
         }
-        const int col = n_blk * BN + c * 32 + lane;
-        if (col < N) {
-#pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int row = row0 + r;
-            if (row >= M) break;
-            const float v = epi_value(e, stg[r * kTcEpiStride + lane], row, col, epi_pe_row(e, row));
-            epi_store(e, v, row, epi_out_row(e, row), col);
+        const int col0 = n_blk * BN + c * 32;
+        if (args.vec4) {
+          const int col = col0 + lc;
+          if (col < N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + lr;
+              const int row = row0 + rr;
+              float4 v = *reinterpret_cast<const float4*>(&stg[rr * kTcEpiStride + lc]);
+              if (row < M) {
+                v.x = (v.x + b4.x) * e.alpha; v.y = (v.y + b4.y) * e.alpha;
+                v.z = (v.z + b4.z) * e.alpha; v.w = (v.w + b4.w) * e.alpha;
+                int out_row = row;
+                if (e.pe || e.row_map) {
+                  const int b = row / e.rows_per_clip, sidx = row - b * e.rows_per_clip;
+                  if (e.pe) {
+                    const int p = e.pe_index ? __ldg(e.pe_index + b) : b;
+                    const float4 pv = __ldg(reinterpret_cast<const float4*>(e.pe + static_cast<size_t>(p) * e.ld_pe + col));
+                    v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+                  }
+                  if (e.row_map == 1) out_row = sidx * e.clips + b;
+                  else if (e.row_map == 2) out_row = (sidx == e.rows_per_clip - 1) ? b : -1;
+                }
+                if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (e.residual) {
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(row) * e.ld_res + col));
+                  v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                }
+                if (e.out32 && out_row >= 0)
+                  *reinterpret_cast<float4*>(e.out32 + static_cast<size_t>(out_row) * e.ld32 + col) = v;
+                if (e.out_hi) {
+                  const float f[4] = {v.x, v.y, v.z, v.w};
+                  uint16_t hi[4], lo[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) { hi[u] = to_plane_hi(f[u], e.bf16); lo[u] = to_plane_lo(f[u], hi[u]); }
+                  const size_t o = static_cast<size_t>(row) * e.ld16 + col;
+                  *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+                  if (e.out_lo)
+                    *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+                }
+              }
+            }
+          }
+        } else {
+          // unaligned / odd-N fallback: one column per lane, one row per pass
+          const int col = col0 + lane;
+          if (col < N) {
+            for (int r = 0; r < 32; ++r) {
+              const int row = row0 + r;
+              if (row >= M) break;
+              const float v = epi_value(e, stg[r * kTcEpiStride + lane], row, col, epi_pe_row(e, row));
+              epi_store(e, v, row, epi_out_row(e, row), col);
+            }
           }
         }
         __syncwarp();
@@ -257,6 +307,18 @@ inline bool make_tmap_2d(CUtensorMap* out, const void* base, int rows, int cols,
   return r == CUDA_SUCCESS;
 }
 
+inline bool epilogue_vec4_ok(const Epilogue& e, int N) {
+  auto al = [](const void* p, int bytes) { return (reinterpret_cast<uintptr_t>(p) % bytes) == 0; };
+  if (N % 4 != 0) return false;
+  if (e.bias && !al(e.bias, 16)) return false;
+  if (e.pe && (!al(e.pe, 16) || e.ld_pe % 4 != 0)) return false;
+  if (e.residual && (!al(e.residual, 16) || e.ld_res % 4 != 0)) return false;
+  if (e.out32 && (!al(e.out32, 16) || e.ld32 % 4 != 0)) return false;
+  if (e.out_hi && (!al(e.out_hi, 8) || e.ld16 % 4 != 0)) return false;
+  if (e.out_lo && !al(e.out_lo, 8)) return false;
+  return true;
+}
+
 template <int BN, bool SPLIT>
 inline cudaError_t launch_gemm_tc_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                                     const CUtensorMap& b_lo, const TcGemmArgs& args, int num_sms,
@@ -271,7 +333,9 @@ inline cudaError_t launch_gemm_tc_t(const CUtensorMap& a_hi, const CUtensorMap& 
   }
   const int tiles = ceil_div(args.M, kTcBM) * ceil_div(args.N, BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN, SPLIT><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, args);
+  TcGemmArgs a2 = args;
+  a2.vec4 = epilogue_vec4_ok(args.epi, args.N) ? 1 : 0;
+  gemm_tc_kernel<BN, SPLIT><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, a2);
   return cudaGetLastError();
 }
 

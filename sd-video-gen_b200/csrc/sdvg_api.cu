@@ -158,7 +158,7 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     if (ok && split) ok = make_tmap_2d(&ta_lo, a_lo, Mp, Kp, Kp, kTcBM, false) && make_tmap_2d(&tb_lo, w_lo, N, Kp, Kp, boxn, false);
     if (!ok) { cleanup(); g_create_error = "sdvg_gemm: cuTensorMapEncodeTiled failed"; return SDVG_ERR_CUDA; }
     if (!split) { ta_lo = ta_hi; tb_lo = tb_hi; }
-    TcGemmArgs args{M, N, K, bf ? 1 : 0, e};
+    TcGemmArgs args{M, N, K, bf ? 1 : 0, 0, e};
     const int sms = prop.multiProcessorCount;
     cudaEventRecord(ev0, st);
     for (int i = 0; i < iters && err == cudaSuccess; ++i) {

@@ -1,0 +1,72 @@
+"""GPU: kernel-level checks through the C ABI (sdvg_gemm) against a float64 torch reference of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+def ref(A, W, bias, relu, precision):
+    if precision in ("fp16", "bf16"):
+        dt = torch.float16 if precision == "fp16" else torch.bfloat16
+        A, W = A.to(dt), W.to(dt)          # the kernel rounds operands to 16 bit, accumulates in fp32
+    y = A.double() @ W.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    return torch.relu(y) if relu else y
+
+
+# tolerance: fp32 accumulation error of a K-long dot product, relative to the output's max
+TOL = {"fp32_simt": 5e-6, "fp32": 1e-5, "fp16": 1e-5, "bf16": 1e-5}
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (77, 96, 32), (300, 520, 2048), (1, 32, 8), (640, 6144, 256),
+                                   (2000, 2048, 2048)])
+def test_gemm_matches_float64(precision, shape):
+    import sdvg_b200
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    for relu in (False, True):
+        C, _ = sdvg_b200.gemm(A, W, b, relu=relu, precision=precision)
+        assert relerr(C, ref(A, W, b, relu, precision)) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision,bns", [("fp16", (32, 64, 128, 256)), ("fp32", (32, 64, 128))])
+def test_gemm_every_tile_width_is_bit_identical(precision, bns):
+    """The accumulation order along K does not depend on the N tile width: all instantiations agree bit for bit."""
+    import sdvg_b200
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(333, 1024, device="cuda", generator=g)
+    W = torch.randn(512, 1024, device="cuda", generator=g) * 0.05
+    outs = [sdvg_b200.gemm(A, W, None, precision=precision, block_n=bn)[0] for bn in bns]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def test_split_gemm_recovers_fp32_operands():
+    """fp16 rounding of the operands costs ~5e-4; the split mode must be >100x closer to the exact product."""
+    import sdvg_b200
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(256, 2048, device="cuda", generator=g) * 30.0     # un-normalised emb*sqrt(d) scale
+    W = torch.randn(512, 2048, device="cuda", generator=g) * 0.02
+    exact = A.double() @ W.double().t()
+    e16 = relerr(sdvg_b200.gemm(A, W, None, precision="fp16")[0], exact)
+    e32 = relerr(sdvg_b200.gemm(A, W, None, precision="fp32")[0], exact)
+    assert e32 < 5e-6 and e16 > 50 * e32
+
+
+def test_gemm_linearity():
+    import sdvg_b200
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(130, 512, device="cuda", generator=g)
+    W = torch.randn(256, 512, device="cuda", generator=g) * 0.05
+    c1 = sdvg_b200.gemm(A, W, None, precision="fp32")[0]
+    c2 = sdvg_b200.gemm(2.0 * A, W, None, precision="fp32")[0]      # power-of-two scaling is exact in every plane
+    assert torch.equal(c2, 2.0 * c1)

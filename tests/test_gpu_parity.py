@@ -1,0 +1,175 @@
+"""GPU: parity of the CUDA path (through the Python mirror -> ctypes -> libsdvg C ABI) against the golden
+outputs of the unmodified reference (tests/golden, made by oracle/make_golden.py) and against the oracle on
+the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): per predicted frame max|ours-ref| / max|ref|
+  fp32 modes  <= 1e-4 free-running          ("fp32" = split fp16x2 operands on tensor cores; "fp32_simt" = CUDA cores)
+  16-bit mode <= 5e-3 teacher-forced        ("mixed" = fp16 operands, embedding + layer-0 QKV in split precision)
+"""
+import pytest
+import torch
+
+import sdvg_b200
+from conftest import load_golden, ref_model_from_golden
+from oracle import functional as F
+from oracle import rollout as R
+
+pytestmark = pytest.mark.gpu
+TOL32, TOL16 = 1e-4, 5e-3
+DEV = "cuda"
+
+
+def maxrel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max())
+
+
+def ours_from(g, precision):
+    ref = ref_model_from_golden(g)
+    d, H, Le, Ld, E = (int(v) for v in g["arch"])
+    m = sdvg_b200.Transformer(0, d, H, Le, Ld, 0.1, frame_size={256: 64, 1024: 128}[E], precision=precision)
+    m.load_state_dict(ref.state_dict())
+    return m.eval().to(DEV), ref
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", TOL32), ("fp32", TOL32), ("mixed", TOL16), ("fp16", TOL16)])
+def test_forward_golden_tiny(precision, tol):
+    """forward(src, tgt, tgt_mask): S_src=6/S_tgt=5 (the trainer's shapes), mask tensor / None / causal, B=64."""
+    g = load_golden("tiny_forward")
+    m, ref = ours_from(g, precision)
+    src, tgt, x64 = g["src"].to(DEV), g["tgt"].to(DEV), g["x64"].to(DEV)
+    with torch.no_grad():
+        assert maxrel(m(src, tgt, ref.get_tgt_mask(5)), g["out_causal"]) < tol      # CPU mask tensor, like predict.py:24
+        assert maxrel(m(src, tgt, ref.get_tgt_mask(5).to(DEV)), g["out_causal"]) < tol
+        assert maxrel(m(src, tgt, "causal"), g["out_causal"]) < tol
+        assert maxrel(m(src, tgt), g["out_nomask"]) < tol
+        assert maxrel(m(src, src, ref.get_tgt_mask(6)), g["out_same"]) < tol
+        assert maxrel(m(src, src.clone(), ref.get_tgt_mask(6)), g["out_same"]) < tol  # src != tgt pointers: no dedupe
+        out = m(x64, x64, "causal")
+        assert tuple(out.shape) == (2, 64, 256)                                       # (S_tgt, B, E)
+        assert maxrel(out, g["out_b64"]) < tol
+
+
+def test_forward_shape_errors_and_b65():
+    g = load_golden("tiny_forward")
+    m, _ = ours_from(g, "fp32")
+    x = torch.zeros(65, 2, 256, device=DEV)
+    with pytest.raises(RuntimeError, match=r"size of tensor a \(65\)"):
+        m(x, x)
+    out = m(x, x, "causal", pe_index=torch.arange(65) % 64)                            # extension: explicit PE rows
+    assert tuple(out.shape) == (2, 65, 256)
+    with pytest.raises(RuntimeError):
+        m(x[:2, :, :100], x[:2, :, :100])
+
+
+def test_pe_indexed_by_batch_position():
+    """the same clip at batch slot 0 vs 2 gives different outputs; pe_index reproduces it."""
+    g = load_golden("tiny_forward")
+    m, ref = ours_from(g, "fp32")
+    src = g["src"].to(DEV)
+    with torch.no_grad():
+        full = m(src, src, "causal")
+        alone = m(src[2:3], src[2:3], "causal", pe_index=torch.tensor([2]))
+        wrong = m(src[2:3], src[2:3], "causal")
+    assert maxrel(alone[:, 0], full[:, 2].cpu()) < 1e-5
+    assert maxrel(wrong[:, 0], full[:, 2].cpu()) > 1e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", TOL32), ("fp32", TOL32), ("mixed", TOL16)])
+def test_forward_golden_d256(precision, tol):
+    g = load_golden("d256_forward")
+    m, _ = ours_from(g, precision)
+    x = g["x"].to(DEV)
+    with torch.no_grad():
+        assert maxrel(m(x, x, "causal"), g["out"]) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+def test_rollout_golden_small_free_running(precision):
+    g = load_golden("small_rollout")
+    m, _ = ours_from(g, precision)
+    ctx = g["ctx"].to(DEV)
+    assert R.max_rel_per_frame(sdvg_b200.rollout(m, ctx, 4, 5).cpu(), g["free5"]).max() < TOL32
+    assert R.max_rel_per_frame(sdvg_b200.rollout(m, ctx, 3, 10).cpu(), g["free10"]).max() < TOL32
+    fa = sdvg_b200.rollout(m, g["frames"].to(DEV), 4, 5, use_sos=True).cpu()          # literal predict.py sequence
+    assert R.max_rel_per_frame(fa, g["faithful"]).max() < TOL32
+    b1 = sdvg_b200.rollout(m, g["frames"][:1].to(DEV), 2, 5, use_sos=True).cpu()      # the reference's B=1 case
+    assert R.max_rel_per_frame(b1, g["faithful_b1"]).max() < TOL32
+    # predict(): clip 0, last position (prediction/predict.py:42)
+    p = sdvg_b200.predict(m, ctx[:, -5:])
+    assert tuple(p.shape) == (256,)
+    assert maxrel(p, g["free5"][0, 0]) < TOL32
+
+
+@pytest.mark.parametrize("precision", ["mixed", "fp16"])
+def test_rollout_golden_small_teacher_forced_16bit(precision):
+    g = load_golden("small_rollout")
+    m, _ = ours_from(g, precision)
+    out = sdvg_b200.rollout(m, g["ctx"].to(DEV), 4, 5, teacher=g["free5"].to(DEV)).cpu()
+    assert R.max_rel_per_frame(out, g["free5"]).max() < TOL16
+
+
+def test_rollout_scales_and_host_path():
+    g = load_golden("small_rollout")
+    m, _ = ours_from(g, "fp32")
+    ctx = g["ctx"].to(DEV)
+    base = sdvg_b200.rollout(m, ctx, 2, 5)
+    s = sdvg_b200.LATENT_SCALE
+    scaled = sdvg_b200.rollout(m, ctx / s, 2, 5, scale_in=s, scale_out=1.0 / s)       # utils/sd_utils.py:143,159
+    assert maxrel(scaled * s, base.cpu()) < 1e-5
+    host = sdvg_b200.rollout_from_host(m, g["ctx"], 2, 5)
+    assert not host.is_cuda and torch.equal(host, base.cpu())
+
+
+def test_rollout_is_deterministic_and_batch_invariant():
+    g = load_golden("small_rollout")
+    m, _ = ours_from(g, "fp32")
+    ctx = torch.randn(200, 6, 256, generator=torch.Generator().manual_seed(3)).to(DEV)
+    a = sdvg_b200.rollout(m, ctx, 2, 5)
+    b = sdvg_b200.rollout(m, ctx, 2, 5)
+    assert torch.equal(a, b)
+    # a clip's result depends only on its own data and its PE row: shards == full batch, bit for bit
+    parts = [sdvg_b200.rollout(m, ctx[s:e], 2, 5, pe_index=sdvg_b200.pe_index_for(s, e)) for s, e in ((0, 64), (64, 128), (128, 200))]
+    assert torch.equal(torch.cat(parts), a)
+
+
+def test_b_gt_64_equals_reference_in_chunks():
+    """B=130 in one call == the reference run in chunks of <= 64 clips (clip i sees PE[i mod 64])."""
+    g = load_golden("small_rollout")
+    m, ref = ours_from(g, "fp32")
+    ctx = torch.randn(130, 6, 256, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = R.chunked(lambda c: R.rollout_ref(ref, c, 2, 5), ctx)
+    got = sdvg_b200.rollout(m, ctx.to(DEV), 2, 5).cpu()
+    assert R.max_rel_per_frame(got, want).max() < TOL32
+
+
+@pytest.mark.parametrize("name", ["c1_rollout", "c4_rollout"])
+def test_full_size_configs_golden(name):
+    """BASELINE configs at full width: C1/C2 arch (d2048 4e/8d E256) and C4 (d2048 6e/6d E1024)."""
+    g = load_golden(name)
+    n = g["free5"].shape[1]
+    m, _ = ours_from(g, "fp32")
+    ctx = g["ctx"].to(DEV)
+    assert R.max_rel_per_frame(sdvg_b200.rollout(m, ctx, n, 5).cpu(), g["free5"]).max() < TOL32
+    if "free10" in g:
+        assert R.max_rel_per_frame(sdvg_b200.rollout(m, ctx, 1, 10).cpu(), g["free10"]).max() < TOL32
+    m.set_precision("mixed")
+    tf = sdvg_b200.rollout(m, ctx, n, 5, teacher=g["free5"].to(DEV)).cpu()
+    assert R.max_rel_per_frame(tf, g["free5"]).max() < TOL16
+
+
+def test_bench_size_batch_properties():
+    """B=1024 clips (BASELINE configs[1] size) on the C1/C2 architecture: no oracle at this size, so check
+    size-independent properties - the first 8 clips equal the golden 8-clip run, and a 64-aligned shard equals
+    the same clips inside the big batch."""
+    g = load_golden("c1_rollout")
+    m, _ = ours_from(g, "fp32")
+    gen = torch.Generator().manual_seed(99)
+    ctx = torch.randn(1024, 10, 256, generator=gen)
+    ctx[:8] = g["ctx"]
+    ctx = ctx.to(DEV)
+    out = sdvg_b200.rollout(m, ctx, 2, 5)
+    assert torch.isfinite(out).all()
+    assert R.max_rel_per_frame(out[:8].cpu(), g["free5"][:, :2]).max() < TOL32
+    shard = sdvg_b200.rollout(m, ctx[512:640], 2, 5, pe_index=sdvg_b200.pe_index_for(512, 640))
+    assert R.max_rel_per_frame(shard.cpu(), out[512:640].cpu()).max() < 1e-5
