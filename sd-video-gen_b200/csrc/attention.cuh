@@ -35,6 +35,9 @@ __device__ __forceinline__ void load_frag(float (&f)[NCH * VEC], const float* __
     if constexpr (VEC == 4) {
       const float4 t = e0 < hd ? __ldg(reinterpret_cast<const float4*>(row + e0)) : make_float4(0.f, 0.f, 0.f, 0.f);
       f[c * 4 + 0] = t.x; f[c * 4 + 1] = t.y; f[c * 4 + 2] = t.z; f[c * 4 + 3] = t.w;
+    } else if constexpr (VEC == 2) {
+      const float2 t = e0 < hd ? __ldg(reinterpret_cast<const float2*>(row + e0)) : make_float2(0.f, 0.f);
+      f[c * 2 + 0] = t.x; f[c * 2 + 1] = t.y;
     } else {
       f[c] = e0 < hd ? __ldg(row + e0) : 0.f;
     }
@@ -129,11 +132,124 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   }
 }
 
+// Fast path (hd == 32 * VEC * NCH exactly, Sk <= SMAX): K and V of the (clip, head) are loaded ONCE into
+// registers with all 128-bit loads in flight together, then every query row is scored from registers.
+// The generic kernel above re-reads K/V per query row through L1 and is latency bound (measured 1.46 TB/s
+// algorithmic on B200 at S=5, hd=256); this one issues 2*Sk*NCH independent loads per lane up front.
+template <int VEC, int NCH, int SMAX>
+__global__ void __launch_bounds__(128) attention_reg_kernel(const __grid_constant__ AttnArgs a) {
+  constexpr int EPL = VEC * NCH;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= a.clips * a.heads) return;
+  const int b = warp_global / a.heads, h = warp_global - b * a.heads;
+  const int hd = a.hd;
+  const float* qb = a.q + static_cast<size_t>(b) * a.Sq * a.ldq + h * hd;
+  const float* kb = a.k + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
+  const float* vb = a.v + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
+  float kr[SMAX][EPL], vr[SMAX][EPL];
+#pragma unroll
+  for (int j = 0; j < SMAX; ++j) {
+    if (j < a.Sk) {
+      load_frag<VEC, NCH>(kr[j], kb + static_cast<size_t>(j) * a.ldkv, hd, lane);
+      load_frag<VEC, NCH>(vr[j], vb + static_cast<size_t>(j) * a.ldkv, hd, lane);
+    }
+  }
+  const float scale2 = a.scale * kLog2e;  // softmax in base 2: exp(x) = exp2(x * log2 e)
+  for (int i = a.q_first; i < a.Sq; ++i) {
+    float ql[EPL];
+    load_frag<VEC, NCH>(ql, qb + static_cast<size_t>(i) * a.ldq, hd, lane);
+    float sc[SMAX];
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+      float part = 0.f;
+      if (j < a.Sk) {
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) part = fmaf(ql[t], kr[j][t], part);
+      }
+      sc[j] = part;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < SMAX; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+      float s = sc[j] * scale2;
+      if (j >= a.Sk) s = -INFINITY;
+      else if (a.mask_kind == 1) { if (j > i + (a.Sk - a.Sq)) s = -INFINITY; }
+      else if (a.mask_kind == 2) s += __ldg(a.mask + i * a.Sk + j) * kLog2e;
+      sc[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+      sc[j] = (j < a.Sk) ? exp2f(sc[j] - mx) : 0.f;
+      sum += sc[j];
+    }
+    const float inv = 1.0f / sum;
+    float ol[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) ol[t] = 0.f;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+      if (j < a.Sk) {
+        const float p = sc[j] * inv;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) ol[t] = fmaf(p, vr[j][t], ol[t]);
+      }
+    }
+    const size_t row = static_cast<size_t>(b) * a.Sq + i;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = h * hd + (c * 32 + lane) * VEC;
+      if (a.out32) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a.out32[row * a.ld32 + col + v] = ol[c * VEC + v];
+      }
+      if (a.out_hi) {
+        uint16_t hi[VEC], lo[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { hi[v] = to_plane_hi(ol[c * VEC + v], a.bf16); lo[v] = to_plane_lo(ol[c * VEC + v], hi[v]); }
+        if constexpr (VEC == 4) {
+          *reinterpret_cast<uint2*>(a.out_hi + row * a.ld16 + col) = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+          if (a.out_lo) *reinterpret_cast<uint2*>(a.out_lo + row * a.ld16 + col) = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+        } else if constexpr (VEC == 2) {
+          *reinterpret_cast<uint32_t*>(a.out_hi + row * a.ld16 + col) = hi[0] | (uint32_t(hi[1]) << 16);
+          if (a.out_lo) *reinterpret_cast<uint32_t*>(a.out_lo + row * a.ld16 + col) = lo[0] | (uint32_t(lo[1]) << 16);
+        } else {
+          a.out_hi[row * a.ld16 + col] = hi[0];
+          if (a.out_lo) a.out_lo[row * a.ld16 + col] = lo[0];
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int NCH>
+inline bool launch_attention_reg(const AttnArgs& a, int grid, cudaStream_t stream) {
+  if (a.Sk <= 6) attention_reg_kernel<VEC, NCH, 6><<<grid, 128, 0, stream>>>(a);
+  else if (a.Sk <= 10) attention_reg_kernel<VEC, NCH, 10><<<grid, 128, 0, stream>>>(a);
+  else return false;
+  return true;
+}
+
 inline cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sk > kAttnMaxS || a.Sq > kAttnMaxS || a.hd > 256) return cudaErrorInvalidValue;
   const int warps = a.clips * a.heads;
   const int grid = ceil_div(warps, 4);
-  const bool vec = (a.hd % 128 == 0) && (a.ldq % 4 == 0) && (a.ldkv % 4 == 0);
+  const bool al4 = (a.ldq % 4 == 0) && (a.ldkv % 4 == 0) && (a.ld32 % 4 == 0);
+  bool done = false;
+  if (al4 && a.hd == 256) done = launch_attention_reg<4, 2>(a, grid, stream);
+  else if (al4 && a.hd == 128) done = launch_attention_reg<4, 1>(a, grid, stream);
+  else if (al4 && a.hd == 64) done = launch_attention_reg<2, 1>(a, grid, stream);
+  else if (al4 && a.hd == 32) done = launch_attention_reg<1, 1>(a, grid, stream);
+  if (done) return cudaGetLastError();
+  const bool vec = (a.hd % 128 == 0) && al4;
   if (vec && a.hd == 128) attention_kernel<4, 1><<<grid, 128, 0, stream>>>(a);
   else if (vec && a.hd == 256) attention_kernel<4, 2><<<grid, 128, 0, stream>>>(a);
   else if (a.hd <= 32) attention_kernel<1, 1><<<grid, 128, 0, stream>>>(a);

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "layernorm.cuh"
 #include "pack.cuh"
 
@@ -24,8 +25,13 @@ namespace sdvg {
 enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_SIMT = 1, KC_ATTN = 2, KC_LN = 3, KC_PACK = 4 };
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-inline int bn_index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3; }
-constexpr int kBnValues[4] = {32, 64, 128, 256};
+// TMA box heights (rows of W per load) we keep tensor maps for: one-CTA tiles use BN rows, pair tiles BN/2.
+constexpr int kNumBoxes = 5;
+constexpr int kBoxRows[kNumBoxes] = {32, 64, 96, 128, 256};
+inline int box_index(int rows) { return rows == 32 ? 0 : rows == 64 ? 1 : rows == 96 ? 2 : rows == 128 ? 3 : 4; }
+
+// A GEMM tile plan: pair = CTA-pair kernel (256 x bn tiles) or one-CTA kernel (128 x bn tiles).
+struct TilePlan { bool pair; int bn; };
 
 // 16-bit operand planes of a matrix [rows][cols] (row pitch ld, zero padded to a multiple of 64 columns so a
 // TMA box never leaves the tensor along K) with their tensor maps.
@@ -33,7 +39,7 @@ struct Planes {
   uint16_t* hi = nullptr;
   uint16_t* lo = nullptr;
   int rows = 0, cols = 0, ld = 0;
-  CUtensorMap tm_hi[4], tm_lo[4];  // activations: [0] only (box 128 rows); weights: one per tile width
+  CUtensorMap tm_hi[kNumBoxes], tm_lo[kNumBoxes];  // activations: [0] only (box 128 rows); weights: one per box height
 };
 
 struct ActBuf {
@@ -155,9 +161,9 @@ class Engine {
       if (p.lo && !make_tmap_2d(&p.tm_lo[0], p.lo, p.rows, p.ld, p.ld, kTcBM, false)) return false;
       return true;
     }
-    for (int i = 0; i < 4; ++i) {
-      if (kBnValues[i] > p.rows && i > 0) { p.tm_hi[i] = p.tm_hi[i - 1]; p.tm_lo[i] = p.tm_lo[i - 1]; continue; }
-      const int box = kBnValues[i] > p.rows ? p.rows : kBnValues[i];
+    for (int i = 0; i < kNumBoxes; ++i) {
+      if (kBoxRows[i] > p.rows && i > 0) { p.tm_hi[i] = p.tm_hi[i - 1]; p.tm_lo[i] = p.tm_lo[i - 1]; continue; }
+      const int box = kBoxRows[i] > p.rows ? p.rows : kBoxRows[i];
       if (!make_tmap_2d(&p.tm_hi[i], p.hi, p.rows, p.ld, p.ld, box, bf16())) return false;
       if (p.lo && !make_tmap_2d(&p.tm_lo[i], p.lo, p.rows, p.ld, p.ld, box, false)) return false;
     }
@@ -419,41 +425,73 @@ class Engine {
   }
 
   // ------------------------------------------------------------------ kernels
-  // Tile width: trade wave quantisation (tiles vs. SM count) against per-tile efficiency.
-  int choose_bn(int M, int N, bool split) const {
-    static const double tile_eff[4] = {0.45, 0.70, 0.90, 1.0};
-    const int m_tiles = ceil_div(M, kTcBM);
-    int best = 32; double best_score = -1.0;
-    for (int i = 0; i < 4; ++i) {
-      const int bn = kBnValues[i];
-      if (split && bn > 128) continue;
-      if (bn > 32 && bn > N) continue;
-      const int tiles = m_tiles * ceil_div(N, bn);
-      const int waves = ceil_div(tiles, num_sms);
-      const double quant = static_cast<double>(tiles) / (static_cast<double>(waves) * num_sms);
-      const double score = quant * tile_eff[i];
-      if (score > best_score) { best_score = score; best = bn; }
+  // Tile plan: trade wave quantisation (tiles vs. SMs / SM pairs) against per-tile efficiency.  The relative
+  // efficiencies are measured on B200 (tools/gpu_check.py gemm_speed, profiles/), normalised to the 256x256 pair tile.
+  TilePlan choose_plan(int M, int N, bool split) const {
+    // per-tile throughput relative to the 256x256 pair tile, measured at 8192^3 (MMA-bound regime) on B200:
+    //   one-CTA 128 x {64,128,256}: 524 / 859 / 1249 TFLOP/s;  pair 256 x {64,128,192,256}: 517 / 882 / 1130 / 1244.
+    // On the model's K=2048 shapes the pair kernel additionally wins on per-launch overhead, hence the 0.92.
+    static const int bn1[4] = {32, 64, 128, 256};
+    static const double eff1[4] = {0.22, 0.42, 0.69, 0.92};
+    static const double eff1s[4] = {0.32, 0.55, 0.85, 0.0};
+    static const int bn2[4] = {64, 128, 192, 256};
+    static const double eff2[4] = {0.42, 0.71, 0.91, 1.0};
+    static const double eff2s[4] = {0.60, 1.0, 0.0, 0.0};
+    TilePlan best{false, 32};
+    double best_cost = 1e300;
+    for (int i = 0; i < 4; ++i) {  // one-CTA 128 x bn: one tile per SM per round
+      const int bn = bn1[i];
+      const double eff = split ? eff1s[i] : eff1[i];
+      if (eff <= 0.0 || (bn > 32 && bn > N)) continue;
+      const int tiles = ceil_div(M, kTcBM) * ceil_div(N, bn);
+      const double cost = ceil_div(tiles, num_sms) * (bn / 256.0) / eff;
+      if (cost < best_cost) { best_cost = cost; best = TilePlan{false, bn}; }
+    }
+    if (M > kTcBM) {
+      for (int i = 0; i < 4; ++i) {  // CTA pair 256 x bn: one tile per SM pair per round
+        const int bn = bn2[i];
+        const double eff = split ? eff2s[i] : eff2[i];
+        if (eff <= 0.0 || bn / 2 > N) continue;
+        const int tiles = ceil_div(M, kTc2BM) * ceil_div(N, bn);
+        const double cost = ceil_div(tiles, num_sms / 2) * (bn / 256.0) / eff;
+        if (cost < best_cost) { best_cost = cost; best = TilePlan{true, bn}; }
+      }
     }
     return best;
   }
 
-  cudaError_t gemm_tc_dispatch(const Planes& A, const Planes& B, bool split, int bn, const TcGemmArgs& args,
+  cudaError_t gemm_tc_dispatch(const Planes& A, const Planes& B, bool split, TilePlan plan, const TcGemmArgs& args,
                                cudaStream_t st) {
-    const int bi = bn_index(bn);
-    const CUtensorMap& alo = split ? A.tm_lo[0] : A.tm_hi[0];
-    const CUtensorMap& blo = split ? B.tm_lo[bi] : B.tm_hi[bi];
+    const int bn = plan.bn;
+    const int bi = box_index(plan.pair ? bn / 2 : bn);
+    const CUtensorMap& ah = A.tm_hi[0];
+    const CUtensorMap& al = split ? A.tm_lo[0] : A.tm_hi[0];
+    const CUtensorMap& bh = B.tm_hi[bi];
+    const CUtensorMap& bl = split ? B.tm_lo[bi] : B.tm_hi[bi];
+    if (plan.pair) {
+      if (split) {
+        if (bn == 64) return launch_gemm_tc2_t<64, true>(ah, al, bh, bl, args, num_sms, st);
+        return launch_gemm_tc2_t<128, true>(ah, al, bh, bl, args, num_sms, st);
+      }
+      switch (bn) {
+        case 64: return launch_gemm_tc2_t<64, false>(ah, al, bh, bl, args, num_sms, st);
+        case 128: return launch_gemm_tc2_t<128, false>(ah, al, bh, bl, args, num_sms, st);
+        case 192: return launch_gemm_tc2_t<192, false>(ah, al, bh, bl, args, num_sms, st);
+        default: return launch_gemm_tc2_t<256, false>(ah, al, bh, bl, args, num_sms, st);
+      }
+    }
     if (split) {
       switch (bn) {
-        case 32: return launch_gemm_tc_t<32, true>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
-        case 64: return launch_gemm_tc_t<64, true>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
-        default: return launch_gemm_tc_t<128, true>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+        case 32: return launch_gemm_tc_t<32, true>(ah, al, bh, bl, args, num_sms, st);
+        case 64: return launch_gemm_tc_t<64, true>(ah, al, bh, bl, args, num_sms, st);
+        default: return launch_gemm_tc_t<128, true>(ah, al, bh, bl, args, num_sms, st);
       }
     }
     switch (bn) {
-      case 32: return launch_gemm_tc_t<32, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
-      case 64: return launch_gemm_tc_t<64, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
-      case 128: return launch_gemm_tc_t<128, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
-      default: return launch_gemm_tc_t<256, false>(A.tm_hi[0], alo, B.tm_hi[bi], blo, args, num_sms, st);
+      case 32: return launch_gemm_tc_t<32, false>(ah, al, bh, bl, args, num_sms, st);
+      case 64: return launch_gemm_tc_t<64, false>(ah, al, bh, bl, args, num_sms, st);
+      case 128: return launch_gemm_tc_t<128, false>(ah, al, bh, bl, args, num_sms, st);
+      default: return launch_gemm_tc_t<256, false>(ah, al, bh, bl, args, num_sms, st);
     }
   }
 
@@ -466,11 +504,11 @@ class Engine {
       return launch_gemm_simt(A.f32, A.ld32, L.w32, L.K, M, L.N, L.K, e, st);
     }
     const bool split = L.split && A.p.lo != nullptr;
-    const int bn = choose_bn(M, L.N, split);
+    const TilePlan plan = choose_plan(M, L.N, split);
     TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, e};
     const double planes = split ? 2.0 : 1.0;
     Scope sc(this, KC_GEMM_TC, flops, 2.0 * planes * (double(M) * L.K + double(L.N) * L.K) + 4.0 * double(M) * L.N, st);
-    return gemm_tc_dispatch(A.p, L.p, split, bn, args, st);
+    return gemm_tc_dispatch(A.p, L.p, split, plan, args, st);
   }
 
   // destination description shared by LN / attention / GEMM epilogues

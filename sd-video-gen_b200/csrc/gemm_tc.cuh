@@ -56,7 +56,169 @@ struct TcGemmArgs {
   Epilogue epi;
 };
 
-template <int BN, bool SPLIT>
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 pack_hi4(const float4& v, int bf16) {
+  if (bf16) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+// lo = fp16((v - fp16(v)) * 2^11), four at a time (fp16 hi planes only)
+__device__ __forceinline__ uint2 pack_lo4(const float4& v, const uint2& hi) {
+  const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+  const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+  const __half2 a = __floats2half2_rn((v.x - h0.x) * kSplitScale, (v.y - h0.y) * kSplitScale);
+  const __half2 b = __floats2half2_rn((v.z - h1.x) * kSplitScale, (v.w - h1.y) * kSplitScale);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+// Epilogue of one accumulator tile for one warp: 32 TMEM lanes (rows row0..row0+31) x BN columns starting at
+// global column col_base.  TMEM -> registers -> padded smem transpose -> row-contiguous 128-bit global accesses.
+// `release()` is called by lane 0 once every TMEM read of the tile has completed (hands the accumulator back
+// to the MMA issuer before the global stores are issued).
+// FANCY = false is the lean path of the 70-odd per-layer GEMMs (bias, ReLU, residual, fp32 / plane outputs);
+// FANCY = true adds what only the embedding and output projections need (scale, positional rows, row remapping).
+// The first version of this routine was one generic loop; ncu showed the four epilogue warps issue-bound on
+// per-element address arithmetic, integer division and generic-space smem accesses (~18 us per 128x256 tile,
+// longer than the tile's MMA main loop), so everything row- or tile-invariant is hoisted and the staging
+// buffer is addressed in the shared window explicitly.
+template <int BN, bool SPLIT, bool FANCY, typename Release>
+__device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* stg, uint32_t tbase, int row0,
+                                                 int col_base, int lane, Release release) {
+  const Epilogue& e = args.epi;
+  const int M = args.M, N = args.N;
+  const uint32_t stg_addr = ptx::smem_u32(stg);
+  if (!args.vec4) {
+    // unaligned / odd-N fallback: one column per lane, one row per pass (never on the model's hot path)
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r0[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
+      if (SPLIT) {
+        uint32_t r1[32];
+        ptx::tmem_ld_32x32b_x32(tbase + BN + c * 32, r1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i])));
+      } else {
+        ptx::tmem_ld_wait();
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(stg_addr + (lane * kTcEpiStride + 4 * j) * 4, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+      if (c == BN / 32 - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) release(); } else { __syncwarp(); }
+      const int col = col_base + c * 32 + lane;
+      if (col < N) {
+        for (int r = 0; r < 32; ++r) {
+          const int row = row0 + r;
+          if (row >= M) break;
+          const float v = epi_value(e, stg[r * kTcEpiStride + lane], row, col, epi_pe_row(e, row));
+          epi_store(e, v, row, epi_out_row(e, row), col);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // transposed read-back: 8 lanes x float4 cover the 32 columns of one row, 4 rows per pass, 8 passes
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+  const int rows_valid = M - row0;  // rows of this warp's slab inside the matrix (>= 32: all)
+  const float* bias = e.bias;
+  const float* residual = e.residual;
+  float* out32 = e.out32;
+  uint16_t* out_hi = e.out_hi;
+  uint16_t* out_lo = e.out_lo;
+  const int relu = e.relu, bf16 = e.bf16;
+  const size_t ld_res = e.ld_res, ld32 = e.ld32, ld16 = e.ld16;
+  const uint32_t rd_addr = stg_addr + (lr * kTcEpiStride + lc) * 4;
+  const uint32_t wr_addr = stg_addr + lane * kTcEpiStride * 4;
+
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r0[32];
+    ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
+    if (SPLIT) {
+      uint32_t r1[32];
+      ptx::tmem_ld_32x32b_x32(tbase + BN + c * 32, r1);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i])));
+    } else {
+      ptx::tmem_ld_wait();
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(wr_addr + 16 * j, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+    if (c == BN / 32 - 1) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) release();
+    } else {
+      __syncwarp();
+    }
+    const int col = col_base + c * 32 + lc;
+    if (col < N) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      // issue every residual load of the chunk before the first use
+      float4 res[8];
+      if (residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + lr;
+          res[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(residual + static_cast<size_t>(row0 + rr) * ld_res + col))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + lr;
+        float4 v = lds128(rd_addr + i * 4 * kTcEpiStride * 4);
+        if (rr < rows_valid) {
+          const int row = row0 + rr;
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          int out_row = row;
+          if constexpr (FANCY) {
+            v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
+            if (e.pe || e.row_map) {
+              const int b = row / e.rows_per_clip, sidx = row - b * e.rows_per_clip;
+              if (e.pe) {
+                const int p = e.pe_index ? __ldg(e.pe_index + b) : b;
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(e.pe + static_cast<size_t>(p) * e.ld_pe + col));
+                v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+              }
+              if (e.row_map == 1) out_row = sidx * e.clips + b;
+              else if (e.row_map == 2) out_row = (sidx == e.rows_per_clip - 1) ? b : -1;
+            }
+          }
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+          if (out32 && out_row >= 0) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(out_row) * ld32 + col) = v;
+          if (out_hi) {
+            const uint2 h = pack_hi4(v, bf16);
+            const size_t o = static_cast<size_t>(row) * ld16 + col;
+            *reinterpret_cast<uint2*>(out_hi + o) = h;
+            if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = pack_lo4(v, h);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// The embedding / output projections are the only GEMMs that scale, add positional rows or remap output rows.
+inline bool epilogue_is_fancy(const Epilogue& e) { return e.alpha != 1.0f || e.pe != nullptr || e.row_map != 0; }
+
+template <int BN, bool SPLIT, bool FANCY>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -170,100 +332,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ------------------------------------------------------------------ epilogue warps (4 x 32 TMEM lanes)
     const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
     float* stg = epi_stage + q * 32 * kTcEpiStride;
-    const Epilogue& e = args.epi;
-    // transposed read-back: 8 lanes x float4 cover the 32 columns of one row, 4 rows per pass, 8 passes
-    const int lr = lane >> 3, lc = (lane & 7) * 4;
     int buf = 0;
     uint32_t buf_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
-      const int row0 = m_blk * kTcBM + q * 32;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r0[32];
-        ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
-        if (SPLIT) {
-          uint32_t r1[32];
-          ptx::tmem_ld_32x32b_x32(tbase + BN + c * 32, r1);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i])));
-        } else {
-          ptx::tmem_ld_wait();
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(&stg[lane * kTcEpiStride + 4 * j]) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-        if (c == BN / 32 - 1) {
-          // all TMEM reads of this tile are done: hand the accumulator back before the global stores
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
-        } else {
-          __syncwarp();
-        }
-        const int col0 = n_blk * BN + c * 32;
-        if (args.vec4) {
-          const int col = col0 + lc;
-          if (col < N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = i * 4 + lr;
-              const int row = row0 + rr;
-              float4 v = *reinterpret_cast<const float4*>(&stg[rr * kTcEpiStride + lc]);
-              if (row < M) {
-                v.x = (v.x + b4.x) * e.alpha; v.y = (v.y + b4.y) * e.alpha;
-                v.z = (v.z + b4.z) * e.alpha; v.w = (v.w + b4.w) * e.alpha;
-                int out_row = row;
-                if (e.pe || e.row_map) {
-                  const int b = row / e.rows_per_clip, sidx = row - b * e.rows_per_clip;
-                  if (e.pe) {
-                    const int p = e.pe_index ? __ldg(e.pe_index + b) : b;
-                    const float4 pv = __ldg(reinterpret_cast<const float4*>(e.pe + static_cast<size_t>(p) * e.ld_pe + col));
-                    v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
-                  }
-                  if (e.row_map == 1) out_row = sidx * e.clips + b;
-                  else if (e.row_map == 2) out_row = (sidx == e.rows_per_clip - 1) ? b : -1;
-                }
-                if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                if (e.residual) {
-                  const float4 rv = __ldg(reinterpret_cast<const float4*>(e.residual + static_cast<size_t>(row) * e.ld_res + col));
-                  v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                }
-                if (e.out32 && out_row >= 0)
-                  *reinterpret_cast<float4*>(e.out32 + static_cast<size_t>(out_row) * e.ld32 + col) = v;
-                if (e.out_hi) {
-                  const float f[4] = {v.x, v.y, v.z, v.w};
-                  uint16_t hi[4], lo[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) { hi[u] = to_plane_hi(f[u], e.bf16); lo[u] = to_plane_lo(f[u], hi[u]); }
-                  const size_t o = static_cast<size_t>(row) * e.ld16 + col;
-                  *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
-                  if (e.out_lo)
-                    *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
-                }
-              }
-            }
-          }
-        } else {
-          // unaligned / odd-N fallback: one column per lane, one row per pass
-          const int col = col0 + lane;
-          if (col < N) {
-            for (int r = 0; r < 32; ++r) {
-              const int row = row0 + r;
-              if (row >= M) break;
-              const float v = epi_value(e, stg[r * kTcEpiStride + lane], row, col, epi_pe_row(e, row));
-              epi_store(e, v, row, epi_out_row(e, row), col);
-            }
-          }
-        }
-        __syncwarp();
-      }
+      uint64_t* done_bar = &tempty_bar[buf];
+      tc_epilogue_tile<BN, SPLIT, FANCY>(args, stg, tbase, m_blk * kTcBM + q * 32, n_blk * BN, lane,
+                                  [done_bar]() { ptx::mbar_arrive(done_bar); });
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   }
@@ -319,14 +397,14 @@ inline bool epilogue_vec4_ok(const Epilogue& e, int N) {
   return true;
 }
 
-template <int BN, bool SPLIT>
-inline cudaError_t launch_gemm_tc_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+template <int BN, bool SPLIT, bool FANCY>
+inline cudaError_t launch_gemm_tc_f(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                                     const CUtensorMap& b_lo, const TcGemmArgs& args, int num_sms,
                                     cudaStream_t stream) {
   using Cfg = TcCfg<BN, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT, FANCY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -335,8 +413,16 @@ inline cudaError_t launch_gemm_tc_t(const CUtensorMap& a_hi, const CUtensorMap& 
   const int grid = tiles < num_sms ? tiles : num_sms;
   TcGemmArgs a2 = args;
   a2.vec4 = epilogue_vec4_ok(args.epi, args.N) ? 1 : 0;
-  gemm_tc_kernel<BN, SPLIT><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, a2);
+  gemm_tc_kernel<BN, SPLIT, FANCY><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, a2);
   return cudaGetLastError();
+}
+
+template <int BN, bool SPLIT>
+inline cudaError_t launch_gemm_tc_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                                    const CUtensorMap& b_lo, const TcGemmArgs& args, int num_sms,
+                                    cudaStream_t stream) {
+  if (epilogue_is_fancy(args.epi)) return launch_gemm_tc_f<BN, SPLIT, true>(a_hi, a_lo, b_hi, b_lo, args, num_sms, stream);
+  return launch_gemm_tc_f<BN, SPLIT, false>(a_hi, a_lo, b_hi, b_lo, args, num_sms, stream);
 }
 
 }  // namespace sdvg

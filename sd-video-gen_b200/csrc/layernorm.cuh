@@ -59,7 +59,7 @@ __device__ __forceinline__ void ln_inplace(float4 (&v)[NV], int d, int lane, con
 }
 
 template <int NV>
-__global__ void __launch_bounds__(128) layernorm_kernel(const __grid_constant__ LnArgs a) {
+__global__ void __launch_bounds__(128, NV <= 16 ? 4 : 2) layernorm_kernel(const __grid_constant__ LnArgs a) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);  // index among processed rows
   const int keep = a.rows_per_clip - a.first_token;

@@ -126,7 +126,7 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     if (prop.major != 10 || !get_encode_fn()) { cleanup(); g_create_error = "sdvg_gemm: needs an sm_100 device"; return SDVG_ERR_CUDA; }
-    const int Kp = round_up(K, kTcBK), Mp = round_up(M, kTcBM);
+    const int Kp = round_up(K, kTcBK), Mp = round_up(M, kTc2BM);
     uint16_t *a_hi = nullptr, *a_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
     auto alloc16 = [&](uint16_t** p, size_t n) {
       if (cudaMalloc(reinterpret_cast<void**>(p), n * 2) != cudaSuccess) return false;
@@ -144,35 +144,23 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     };
     err = pack16(A, M, a_hi, a_lo);
     if (err == cudaSuccess) err = pack16(W, N, w_hi, w_lo);
-    int bn = block_n;
-    if (bn == 0) {
-      Engine tmp_eng; tmp_eng.num_sms = prop.multiProcessorCount;
-      bn = tmp_eng.choose_bn(M, N, split);
-    }
-    if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256) || (split && bn == 256) || (bn > N && bn > 32)) {
-      cleanup(); g_create_error = "sdvg_gemm: bad block_n"; return SDVG_ERR_INVALID;
-    }
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    const int boxn = bn > N ? N : bn;
-    ok = make_tmap_2d(&ta_hi, a_hi, Mp, Kp, Kp, kTcBM, bf) && make_tmap_2d(&tb_hi, w_hi, N, Kp, Kp, boxn, bf);
-    if (ok && split) ok = make_tmap_2d(&ta_lo, a_lo, Mp, Kp, Kp, kTcBM, false) && make_tmap_2d(&tb_lo, w_lo, N, Kp, Kp, boxn, false);
+    Engine tmp_eng;
+    tmp_eng.num_sms = prop.multiProcessorCount;
+    tmp_eng.cfg.precision = precision;
+    TilePlan plan = block_n == 0 ? tmp_eng.choose_plan(M, N, split) : TilePlan{block_n < 0, block_n < 0 ? -block_n : block_n};
+    const int bn = plan.bn;
+    const bool ok1 = !plan.pair && (bn == 32 || bn == 64 || bn == 128 || bn == 256) && !(split && bn == 256) && !(bn > N && bn > 32);
+    const bool ok2 = plan.pair && (bn == 64 || bn == 128 || bn == 192 || bn == 256) && !(split && bn > 128) && bn / 2 <= N;
+    if (!ok1 && !ok2) { cleanup(); g_create_error = "sdvg_gemm: bad block_n"; return SDVG_ERR_INVALID; }
+    Planes pa, pb;
+    const int box = plan.pair ? bn / 2 : (bn > N ? N : bn);
+    const int bi = box_index(plan.pair ? bn / 2 : bn);
+    ok = make_tmap_2d(&pa.tm_hi[0], a_hi, Mp, Kp, Kp, kTcBM, bf) && make_tmap_2d(&pb.tm_hi[bi], w_hi, N, Kp, Kp, box, bf);
+    if (ok && split) ok = make_tmap_2d(&pa.tm_lo[0], a_lo, Mp, Kp, Kp, kTcBM, false) && make_tmap_2d(&pb.tm_lo[bi], w_lo, N, Kp, Kp, box, false);
     if (!ok) { cleanup(); g_create_error = "sdvg_gemm: cuTensorMapEncodeTiled failed"; return SDVG_ERR_CUDA; }
-    if (!split) { ta_lo = ta_hi; tb_lo = tb_hi; }
     TcGemmArgs args{M, N, K, bf ? 1 : 0, 0, e};
-    const int sms = prop.multiProcessorCount;
     cudaEventRecord(ev0, st);
-    for (int i = 0; i < iters && err == cudaSuccess; ++i) {
-      if (split) {
-        if (bn == 32) err = launch_gemm_tc_t<32, true>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-        else if (bn == 64) err = launch_gemm_tc_t<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-        else err = launch_gemm_tc_t<128, true>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-      } else {
-        if (bn == 32) err = launch_gemm_tc_t<32, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-        else if (bn == 64) err = launch_gemm_tc_t<64, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-        else if (bn == 128) err = launch_gemm_tc_t<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-        else err = launch_gemm_tc_t<256, false>(ta_hi, ta_lo, tb_hi, tb_lo, args, sms, st);
-      }
-    }
+    for (int i = 0; i < iters && err == cudaSuccess; ++i) err = tmp_eng.gemm_tc_dispatch(pa, pb, split, plan, args, st);
     cudaEventRecord(ev1, st);
   }
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);

@@ -38,9 +38,11 @@ def test_gemm_matches_float64(precision, shape):
         assert relerr(C, ref(A, W, b, relu, precision)) < TOL[precision]
 
 
-@pytest.mark.parametrize("precision,bns", [("fp16", (32, 64, 128, 256)), ("fp32", (32, 64, 128))])
+@pytest.mark.parametrize("precision,bns", [("fp16", (32, 64, 128, 256, -64, -128, -192, -256)),
+                                           ("fp32", (32, 64, 128, -64, -128))])
 def test_gemm_every_tile_width_is_bit_identical(precision, bns):
-    """The accumulation order along K does not depend on the N tile width: all instantiations agree bit for bit."""
+    """The accumulation order along K does not depend on the tile shape: every instantiation of the one-CTA
+    kernel (block_n > 0) and of the CTA-pair kernel (block_n < 0) agrees bit for bit."""
     import sdvg_b200
     g = torch.Generator(device="cuda").manual_seed(3)
     A = torch.randn(333, 1024, device="cuda", generator=g)

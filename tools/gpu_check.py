@@ -42,10 +42,10 @@ def check_gemm_pattern():
     """Layout probe: A rows are unit vectors, so C[i,n] = W[n, i % K] exactly in any precision."""
     import torch, sdvg_b200
     for prec in ("fp16", "fp32"):
-        for bn in (32, 64, 128, 256):
-            if prec == "fp32" and bn == 256:
+        for bn in (32, 64, 128, 256, -64, -128, -192, -256):
+            if prec == "fp32" and abs(bn) > 128:
                 continue
-            M, N, K = 128, 256, 64
+            M, N, K = (128, 256, 64) if bn > 0 else (512, 384, 128)
             A = torch.zeros(M, K, device="cuda"); A[torch.arange(M), torch.arange(M) % K] = 1.0
             W = (torch.arange(N * K, device="cuda", dtype=torch.float32).view(N, K) % 251) / 16.0
             C, _ = sdvg_b200.gemm(A, W, None, precision=prec, block_n=bn)
@@ -67,8 +67,8 @@ def check_gemm_tc():
         for (M, N, K) in shapes:
             A = torch.randn(M, K, device="cuda", generator=g); W = torch.randn(N, K, device="cuda", generator=g) * 0.05
             b = torch.randn(N, device="cuda", generator=g)
-            for bn in (0, 32, 64, 128, 256):
-                if (prec == "fp32" and bn == 256) or (bn > N and bn > 32):
+            for bn in (0, 32, 64, 128, 256, -64, -128, -192, -256):
+                if (prec == "fp32" and abs(bn) > 128) or (bn > N and bn > 32) or (-bn // 2 > N):
                     continue
                 C, _ = sdvg_b200.gemm(A, W, b, relu=False, precision=prec, block_n=bn)
                 e = relerr(C, ref_gemm(A, W, b, False, prec))
@@ -78,11 +78,11 @@ def check_gemm_tc():
 def check_gemm_speed():
     import torch, sdvg_b200
     g = torch.Generator(device="cuda").manual_seed(0)
-    for (M, N, K) in ((5120, 6144, 2048), (5120, 2048, 2048), (10240, 2048, 2048), (8192, 8192, 8192), (40, 6144, 2048), (80, 2048, 2048)):
+    for (M, N, K) in ((5120, 6144, 2048), (5120, 2048, 2048), (5120, 4096, 2048), (10240, 2048, 2048), (8192, 8192, 8192), (5120, 2048, 256), (5120, 256, 2048), (40, 6144, 2048), (80, 2048, 2048)):
         A = torch.randn(M, K, device="cuda", generator=g); W = torch.randn(N, K, device="cuda", generator=g) * 0.05
         for prec in ("fp16", "fp32"):
-            for bn in (32, 64, 128, 256):
-                if prec == "fp32" and bn == 256:
+            for bn in (64, 128, 256, -64, -128, -192, -256, 0):
+                if prec == "fp32" and abs(bn) > 128:
                     continue
                 sdvg_b200.gemm(A, W, None, precision=prec, block_n=bn, iters=2)
                 _, ms = sdvg_b200.gemm(A, W, None, precision=prec, block_n=bn, iters=10)
