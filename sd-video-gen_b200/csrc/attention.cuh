@@ -47,6 +47,8 @@ __device__ __forceinline__ void load_frag(float (&f)[NCH * VEC], const float* __
 template <int VEC, int NCH>
 __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ AttnArgs a) {
   constexpr int EPL = VEC * NCH;
+  pdl_wait();
+  pdl_trigger();
   const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (warp_global >= a.clips * a.heads) return;
@@ -140,6 +142,8 @@ template <int VEC, int NCH, int SMAX>
 __global__ void __launch_bounds__(128) attention_reg_kernel(const __grid_constant__ AttnArgs a) {
   constexpr int EPL = VEC * NCH;
   constexpr float kLog2e = 1.4426950408889634f;
+  pdl_wait();
+  pdl_trigger();
   const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (warp_global >= a.clips * a.heads) return;
@@ -230,12 +234,12 @@ __global__ void __launch_bounds__(128) attention_reg_kernel(const __grid_constan
   }
 }
 
+// returns cudaErrorNotSupported when Sk is beyond the register-resident variants (caller falls back)
 template <int VEC, int NCH>
-inline bool launch_attention_reg(const AttnArgs& a, int grid, cudaStream_t stream) {
-  if (a.Sk <= 6) attention_reg_kernel<VEC, NCH, 6><<<grid, 128, 0, stream>>>(a);
-  else if (a.Sk <= 10) attention_reg_kernel<VEC, NCH, 10><<<grid, 128, 0, stream>>>(a);
-  else return false;
-  return true;
+inline cudaError_t launch_attention_reg(const AttnArgs& a, int grid, cudaStream_t stream) {
+  if (a.Sk <= 6) return launch_kernel(attention_reg_kernel<VEC, NCH, 6>, dim3(grid), dim3(128), 0, stream, a);
+  if (a.Sk <= 10) return launch_kernel(attention_reg_kernel<VEC, NCH, 10>, dim3(grid), dim3(128), 0, stream, a);
+  return cudaErrorNotSupported;
 }
 
 inline cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
@@ -243,20 +247,19 @@ inline cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   const int warps = a.clips * a.heads;
   const int grid = ceil_div(warps, 4);
   const bool al4 = (a.ldq % 4 == 0) && (a.ldkv % 4 == 0) && (a.ld32 % 4 == 0);
-  bool done = false;
-  if (al4 && a.hd == 256) done = launch_attention_reg<4, 2>(a, grid, stream);
-  else if (al4 && a.hd == 128) done = launch_attention_reg<4, 1>(a, grid, stream);
-  else if (al4 && a.hd == 64) done = launch_attention_reg<2, 1>(a, grid, stream);
-  else if (al4 && a.hd == 32) done = launch_attention_reg<1, 1>(a, grid, stream);
-  if (done) return cudaGetLastError();
+  cudaError_t fast = cudaErrorNotSupported;
+  if (al4 && a.hd == 256) fast = launch_attention_reg<4, 2>(a, grid, stream);
+  else if (al4 && a.hd == 128) fast = launch_attention_reg<4, 1>(a, grid, stream);
+  else if (al4 && a.hd == 64) fast = launch_attention_reg<2, 1>(a, grid, stream);
+  else if (al4 && a.hd == 32) fast = launch_attention_reg<1, 1>(a, grid, stream);
+  if (fast != cudaErrorNotSupported) return fast;
   const bool vec = (a.hd % 128 == 0) && al4;
-  if (vec && a.hd == 128) attention_kernel<4, 1><<<grid, 128, 0, stream>>>(a);
-  else if (vec && a.hd == 256) attention_kernel<4, 2><<<grid, 128, 0, stream>>>(a);
-  else if (a.hd <= 32) attention_kernel<1, 1><<<grid, 128, 0, stream>>>(a);
-  else if (a.hd <= 64) attention_kernel<1, 2><<<grid, 128, 0, stream>>>(a);
-  else if (a.hd <= 128) attention_kernel<1, 4><<<grid, 128, 0, stream>>>(a);
-  else attention_kernel<1, 8><<<grid, 128, 0, stream>>>(a);
-  return cudaGetLastError();
+  if (vec && a.hd == 128) return launch_kernel(attention_kernel<4, 1>, dim3(grid), dim3(128), 0, stream, a);
+  else if (vec && a.hd == 256) return launch_kernel(attention_kernel<4, 2>, dim3(grid), dim3(128), 0, stream, a);
+  else if (a.hd <= 32) return launch_kernel(attention_kernel<1, 1>, dim3(grid), dim3(128), 0, stream, a);
+  else if (a.hd <= 64) return launch_kernel(attention_kernel<1, 2>, dim3(grid), dim3(128), 0, stream, a);
+  else if (a.hd <= 128) return launch_kernel(attention_kernel<1, 4>, dim3(grid), dim3(128), 0, stream, a);
+  else return launch_kernel(attention_kernel<1, 8>, dim3(grid), dim3(128), 0, stream, a);
 }
 
 }  // namespace sdvg

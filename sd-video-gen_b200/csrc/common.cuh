@@ -86,4 +86,29 @@ __device__ __forceinline__ void epi_store(const Epilogue& e, float v, int row, i
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The rollout is a chain of ~130 dependent kernels per model pass, many of
+// them 10-50 us long, so the kernel-boundary bubble (launch latency + drain + the next kernel's prologue:
+// mbarrier init, TMEM allocation, tensor-map prefetch, cluster sync) is a measurable share of the step.  Every
+// kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization; it runs its prologue, then
+// pdl_wait() blocks until the previous kernel has completed and flushed (so all data hazards are exactly those
+// of plain stream order), then pdl_trigger() lets the next kernel's CTAs be scheduled as SM resources free up.
+inline bool& pdl_enabled() { static bool on = true; return on; }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace sdvg

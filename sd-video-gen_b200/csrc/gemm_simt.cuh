@@ -11,6 +11,8 @@ constexpr int kSimtBM = 64, kSimtBN = 64, kSimtBK = 16;
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, int lda,
                                                         const float* __restrict__ W, int ldw, int M, int N, int K,
                                                         const __grid_constant__ Epilogue e) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sA[kSimtBK][kSimtBM + 4];
   __shared__ float sW[kSimtBK][kSimtBN + 4];
   const int tid = threadIdx.x;
@@ -60,8 +62,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
 inline cudaError_t launch_gemm_simt(const float* A, int lda, const float* W, int ldw, int M, int N, int K,
                                     const Epilogue& e, cudaStream_t stream) {
   dim3 grid(ceil_div(N, kSimtBN), ceil_div(M, kSimtBM));
-  gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, M, N, K, e);
-  return cudaGetLastError();
+  return launch_kernel(gemm_simt_kernel, dim3(grid), dim3(256), 0, stream, A, lda, W, ldw, M, N, K, e);
 }
 
 }  // namespace sdvg

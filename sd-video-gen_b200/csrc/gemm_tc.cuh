@@ -268,6 +268,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only smem / TMEM / kernel parameters: it may overlap the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
@@ -413,8 +416,7 @@ inline cudaError_t launch_gemm_tc_f(const CUtensorMap& a_hi, const CUtensorMap& 
   const int grid = tiles < num_sms ? tiles : num_sms;
   TcGemmArgs a2 = args;
   a2.vec4 = epilogue_vec4_ok(args.epi, args.N) ? 1 : 0;
-  gemm_tc_kernel<BN, SPLIT, FANCY><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, a2);
-  return cudaGetLastError();
+  return launch_kernel(gemm_tc_kernel<BN, SPLIT, FANCY>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, a_hi, a_lo, b_hi, b_lo, a2);
 }
 
 template <int BN, bool SPLIT>

@@ -97,6 +97,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   ptx::cluster_sync_all();  // peer barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above overlaps the previous kernel's tail (see common.cuh)
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane per CTA)
@@ -204,8 +206,7 @@ inline cudaError_t launch_gemm_tc2_f(const CUtensorMap& a_hi, const CUtensorMap&
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   TcGemmArgs a2 = args;
   a2.vec4 = epilogue_vec4_ok(args.epi, args.N) ? 1 : 0;
-  gemm_tc2_kernel<BN, SPLIT, FANCY><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, a2);
-  return cudaGetLastError();
+  return launch_kernel(gemm_tc2_kernel<BN, SPLIT, FANCY>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, a_hi, a_lo, b_hi, b_lo, a2);
 }
 
 template <int BN, bool SPLIT>

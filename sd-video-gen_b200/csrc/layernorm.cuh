@@ -60,6 +60,8 @@ __device__ __forceinline__ void ln_inplace(float4 (&v)[NV], int d, int lane, con
 
 template <int NV>
 __global__ void __launch_bounds__(128, NV <= 16 ? 4 : 2) layernorm_kernel(const __grid_constant__ LnArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);  // index among processed rows
   const int keep = a.rows_per_clip - a.first_token;
@@ -102,13 +104,12 @@ inline cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   const int grid = ceil_div(nrows, 4);
   if (grid == 0) return cudaSuccess;
   const int nv = ceil_div(a.d, 128);
-  if (nv <= 1) layernorm_kernel<1><<<grid, 128, 0, stream>>>(a);
-  else if (nv <= 2) layernorm_kernel<2><<<grid, 128, 0, stream>>>(a);
-  else if (nv <= 4) layernorm_kernel<4><<<grid, 128, 0, stream>>>(a);
-  else if (nv <= 8) layernorm_kernel<8><<<grid, 128, 0, stream>>>(a);
-  else if (nv <= 16) layernorm_kernel<16><<<grid, 128, 0, stream>>>(a);
-  else layernorm_kernel<32><<<grid, 128, 0, stream>>>(a);
-  return cudaGetLastError();
+  if (nv <= 1) return launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(128), 0, stream, a);
+  else if (nv <= 2) return launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(128), 0, stream, a);
+  else if (nv <= 4) return launch_kernel(layernorm_kernel<4>, dim3(grid), dim3(128), 0, stream, a);
+  else if (nv <= 8) return launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(128), 0, stream, a);
+  else if (nv <= 16) return launch_kernel(layernorm_kernel<16>, dim3(grid), dim3(128), 0, stream, a);
+  else return launch_kernel(layernorm_kernel<32>, dim3(grid), dim3(128), 0, stream, a);
 }
 
 }  // namespace sdvg

@@ -23,6 +23,8 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int w4 = a.width >> 2;
   const long long total = static_cast<long long>(a.clips) * a.tokens * w4;
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
@@ -58,8 +60,7 @@ inline cudaError_t launch_pack(const PackArgs& a, int num_sms, cudaStream_t stre
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms) * 8;
   if (blocks > cap) blocks = cap;
-  pack_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(a);
-  return cudaGetLastError();
+  return launch_kernel(pack_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a);
 }
 
 }  // namespace sdvg

@@ -1,4 +1,5 @@
 // C ABI of libsdvg.so (declared in include/sdvg.h).  Thin, exception-free shims over sdvg::Engine.
+#include <cstdlib>
 #include <new>
 
 #include "engine.cuh"
@@ -11,6 +12,12 @@ struct sdvg_handle {
 
 static thread_local std::string g_create_error;
 
+// SDVG_PDL=0 in the environment disables programmatic dependent launch (A/B measurements); default on.
+static void read_env_options() {
+  const char* v = std::getenv("SDVG_PDL");
+  if (v) sdvg::pdl_enabled() = std::atoi(v) != 0;
+}
+
 extern "C" {
 
 int sdvg_version(void) { return SDVG_VERSION; }
@@ -20,6 +27,7 @@ const char* sdvg_last_error(const sdvg_handle* h) { return h ? h->eng.err.c_str(
 int sdvg_create(const sdvg_config* cfg, sdvg_handle** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return SDVG_ERR_INVALID; }
   *out = nullptr;
+  read_env_options();
   sdvg_handle* h = new (std::nothrow) sdvg_handle();
   if (!h) { g_create_error = "out of host memory"; return SDVG_ERR_INVALID; }
   int r;
@@ -107,6 +115,7 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
   using namespace sdvg;
   if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0) { g_create_error = "sdvg_gemm: bad argument"; return SDVG_ERR_INVALID; }
   if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "sdvg_gemm: no such CUDA device"; return SDVG_ERR_CUDA; }
+  read_env_options();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (iters < 1) iters = 1;
   Epilogue e;
