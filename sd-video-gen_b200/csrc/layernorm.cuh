@@ -97,12 +97,105 @@ __global__ void __launch_bounds__(128, NV <= 16 ? 4 : 2) layernorm_kernel(const 
   }
 }
 
+// Block-per-row variant for wide rows (d = 512 * NV4): 128 threads share one row, NV4 float4 per thread, all
+// loads issued up front, two block reductions (mean, centred variance).  ncu r1b showed the warp-per-row kernel
+// at d=2048 holding 64 values per lane in 128 registers: 14 resident warps per SM, ~2100 instructions per row,
+// issue-bound at 48 % issue utilisation and ~4 TB/s.  This one keeps 16 values per thread (~40 registers).
+__device__ __forceinline__ float block_sum_128(float v, float* red, int lane, int warp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const float t = (red[0] + red[1]) + (red[2] + red[3]);
+  __syncthreads();
+  return t;
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(128) layernorm_block_kernel(const __grid_constant__ LnArgs a) {
+  __shared__ float red[4];
+  pdl_wait();
+  pdl_trigger();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int keep = a.rows_per_clip - a.first_token;
+  const int r = blockIdx.x;
+  const int clip = r / keep, tok = a.first_token + (r - clip * keep);
+  const size_t in_row = static_cast<size_t>(clip) * a.rows_per_clip + tok;
+  const size_t out_row = a.compact ? static_cast<size_t>(r) : in_row;
+  const float inv_d = 1.0f / static_cast<float>(a.d);
+  float4 v[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) v[i] = *reinterpret_cast<const float4*>(a.x + in_row * a.ldx + (i * 128 + tid) * 4);
+  const float* ws[2] = {a.w1, a.w2};
+  const float* bs[2] = {a.b1, a.b2};
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && !a.w2) break;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = block_sum_128(s, red, lane, warp) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float rstd = rsqrtf(block_sum_128(q, red, lane, warp) * inv_d + a.eps);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = (i * 128 + tid) * 4;
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(ws[pass] + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bs[pass] + c));
+      v[i].x = (v[i].x - mean) * rstd * ww.x + bb.x;
+      v[i].y = (v[i].y - mean) * rstd * ww.y + bb.y;
+      v[i].z = (v[i].z - mean) * rstd * ww.z + bb.z;
+      v[i].w = (v[i].w - mean) * rstd * ww.w + bb.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (i * 128 + tid) * 4;
+    if (a.out32) *reinterpret_cast<float4*>(a.out32 + out_row * a.ld32 + c) = v[i];
+    if (a.out_hi) {
+      uint2 h;
+      if (a.bf16) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i].x, v[i].y), p1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+        h = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+      } else {
+        const __half2 p0 = __floats2half2_rn(v[i].x, v[i].y), p1 = __floats2half2_rn(v[i].z, v[i].w);
+        h = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+      }
+      *reinterpret_cast<uint2*>(a.out_hi + out_row * a.ld16 + c) = h;
+      if (a.out_lo) {
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+        const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        const __half2 l0 = __floats2half2_rn((v[i].x - h0.x) * kSplitScale, (v[i].y - h0.y) * kSplitScale);
+        const __half2 l1 = __floats2half2_rn((v[i].z - h1.x) * kSplitScale, (v[i].w - h1.y) * kSplitScale);
+        *reinterpret_cast<uint2*>(a.out_lo + out_row * a.ld16 + c) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
+    }
+  }
+}
+
 inline cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if (a.d % 4 != 0 || a.d > 4096) return cudaErrorInvalidValue;
   const int keep = a.rows_per_clip - a.first_token;
   const int nrows = (a.rows / a.rows_per_clip) * keep;
+  if (nrows == 0) return cudaSuccess;
+  if (a.d % 512 == 0 && a.ldx % 4 == 0) {
+    switch (a.d / 512) {
+      case 1: return launch_kernel(layernorm_block_kernel<1>, dim3(nrows), dim3(128), 0, stream, a);
+      case 2: return launch_kernel(layernorm_block_kernel<2>, dim3(nrows), dim3(128), 0, stream, a);
+      case 3: return launch_kernel(layernorm_block_kernel<3>, dim3(nrows), dim3(128), 0, stream, a);
+      case 4: return launch_kernel(layernorm_block_kernel<4>, dim3(nrows), dim3(128), 0, stream, a);
+      case 6: return launch_kernel(layernorm_block_kernel<6>, dim3(nrows), dim3(128), 0, stream, a);
+      case 8: return launch_kernel(layernorm_block_kernel<8>, dim3(nrows), dim3(128), 0, stream, a);
+      default: break;
+    }
+  }
   const int grid = ceil_div(nrows, 4);
-  if (grid == 0) return cudaSuccess;
   const int nv = ceil_div(a.d, 128);
   if (nv <= 1) return launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(128), 0, stream, a);
   else if (nv <= 2) return launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(128), 0, stream, a);
