@@ -45,7 +45,7 @@ def parse():
     p.add_argument("--context", type=int, default=10)
     p.add_argument("--pred", type=int, default=10)
     p.add_argument("--window", type=int, default=5)
-    p.add_argument("--precision", default="fp16", choices=["fp32_simt", "fp32", "fp16", "bf16", "mixed"])
+    p.add_argument("--precision", default="mixed", choices=["fp32_simt", "fp32", "fp16", "bf16", "mixed"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-steps", type=int, default=2)
     return p.parse_args()

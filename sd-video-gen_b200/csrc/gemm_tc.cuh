@@ -26,7 +26,8 @@ namespace sdvg {
 
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int kTcEpiWarps = 8;
 constexpr int kTcEpiStride = 36;  // floats; 32x32 transpose tile, padded to keep 128-bit accesses conflict-free
 constexpr int kTcSmemLimit = 232448;  // 227 KB
 
@@ -38,7 +39,9 @@ struct TcCfg {
   static constexpr int kABytes = kTcBM * kTcBK * 2;
   static constexpr int kBBytes = BN * kTcBK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kEpiBytes = 4 * 32 * kTcEpiStride * 4;
+  static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4;
+  // epilogue warps that take part: two per quadrant split the tile's 32-column chunks (one per quadrant if BN == 32)
+  static constexpr int kEpiActive = BN >= 64 ? 8 : 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxStages = (kTcSmemLimit - 1024 /*align slack*/ - kEpiBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -49,10 +52,18 @@ struct TcCfg {
   static_assert(kTmemCols <= 512, "TMEM");
 };
 
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SDVG_TRACE(slot) do { if (args.trace && blockIdx.x == 0) args.trace[slot] = global_timer(); } while (0)
+
 struct TcGemmArgs {
   int M, N, K;
   int bf16;  // operand format of the hi planes
   int vec4;  // all epilogue pointers / pitches are 16-byte aligned and N % 4 == 0 (set by the launcher)
+  unsigned long long* trace;  // optional [64] device buffer: CTA 0 records %globaltimer at pipeline events (tools/gemm_trace.py)
   Epilogue epi;
 };
 
@@ -93,14 +104,14 @@ __device__ __forceinline__ uint2 pack_lo4(const float4& v, const uint2& hi) {
 // buffer is addressed in the shared window explicitly.
 template <int BN, bool SPLIT, bool FANCY, typename Release>
 __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* stg, uint32_t tbase, int row0,
-                                                 int col_base, int lane, Release release) {
+                                                 int col_base, int lane, int c_begin, int c_end, Release release) {
   const Epilogue& e = args.epi;
   const int M = args.M, N = args.N;
   const uint32_t stg_addr = ptx::smem_u32(stg);
   if (!args.vec4) {
     // unaligned / odd-N fallback: one column per lane, one row per pass (never on the model's hot path)
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       uint32_t r0[32];
       ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
       if (SPLIT) {
@@ -114,7 +125,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(stg_addr + (lane * kTcEpiStride + 4 * j) * 4, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-      if (c == BN / 32 - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) release(); } else { __syncwarp(); }
+      if (c == c_end - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) release(); } else { __syncwarp(); }
       const int col = col_base + c * 32 + lane;
       if (col < N) {
         for (int r = 0; r < 32; ++r) {
@@ -142,8 +153,29 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
   const uint32_t rd_addr = stg_addr + (lr * kTcEpiStride + lc) * 4;
   const uint32_t wr_addr = stg_addr + lane * kTcEpiStride * 4;
 
+  // software pipeline over the 32-column chunks: the bias and residual loads of chunk c+1 are in flight while
+  // chunk c is transposed and stored (the residual comes from L2 at ~1 us latency; serialising it per chunk made
+  // the epilogue ~8 us per 128x256 tile, all of it exposed on the last tile of every launch)
+  float4 b4_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 res_n[8];
+  auto prefetch = [&](int c) {
+    const int col = col_base + c * 32 + lc;
+    if (col < N) {
+      if (bias) b4_n = __ldg(reinterpret_cast<const float4*>(bias + col));
+      if (residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + lr;
+          res_n[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(residual + static_cast<size_t>(row0 + rr) * ld_res + col))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  };
+  if (c_begin < c_end) prefetch(c_begin);
+
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t r0[32];
     ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
     if (SPLIT) {
@@ -157,27 +189,20 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) sts128(wr_addr + 16 * j, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-    if (c == BN / 32 - 1) {
+    if (c == c_end - 1) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) release();
     } else {
       __syncwarp();
     }
+    const float4 b4 = b4_n;
+    float4 res[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = res_n[i];
+    if (c + 1 < c_end) prefetch(c + 1);
     const int col = col_base + c * 32 + lc;
     if (col < N) {
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
-      // issue every residual load of the chunk before the first use
-      float4 res[8];
-      if (residual) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + lr;
-          res[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(residual + static_cast<size_t>(row0 + rr) * ld_res + col))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + lr;
@@ -250,7 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
-      ptx::mbar_init(&tempty_bar[b], 4);
+      ptx::mbar_init(&tempty_bar[b], Cfg::kEpiActive);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
@@ -332,19 +357,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (4 x 32 TMEM lanes)
-    const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
-    float* stg = epi_stage + q * 32 * kTcEpiStride;
+    // ------------------------------------------------------------------ epilogue warps (2 per 32-lane TMEM quadrant)
+    const int q = warp & 3;               // TMEM lane quadrant this warp is allowed to read
+    const int half = (warp - 2) >> 2;     // which half of the tile's column chunks
+    constexpr int kChunks = BN / 32;
+    const int c_begin = Cfg::kEpiActive == 8 ? half * (kChunks / 2) : 0;
+    const int c_end = Cfg::kEpiActive == 8 ? (half + 1) * (kChunks / 2) : (half == 0 ? kChunks : 0);
+    float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < total_tiles && c_begin < c_end; t += gridDim.x) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
       uint64_t* done_bar = &tempty_bar[buf];
-      tc_epilogue_tile<BN, SPLIT, FANCY>(args, stg, tbase, m_blk * kTcBM + q * 32, n_blk * BN, lane,
-                                  [done_bar]() { ptx::mbar_arrive(done_bar); });
+      tc_epilogue_tile<BN, SPLIT, FANCY>(args, stg, tbase, m_blk * kTcBM + q * 32, n_blk * BN, lane, c_begin, c_end,
+                                         [done_bar]() { ptx::mbar_arrive(done_bar); });
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   }

@@ -11,8 +11,9 @@
 //                       barrier (count 2: one arrive.expect_tx per CTA)
 //   warp 1 (leader)   : issues tcgen05.mma.cta_group::2 (M=256, N=BN, K=16); tcgen05.commit ... multicast
 //                       releases the smem stage / publishes the accumulator in BOTH CTAs
-//   warps 2-5 (both)  : epilogue of the CTA's own 128 accumulator rows (shared with gemm_tc.cuh); they hand the
-//                       TMEM buffer back by arriving on the leader's barrier (count 8)
+//   warps 2-9 (both)  : epilogue of the CTA's own 128 accumulator rows, two warps per TMEM lane quadrant (code
+//                       shared with gemm_tc.cuh); they hand the TMEM buffer back by arriving on the leader's
+//                       barrier (count 16)
 // BN in {64, 128, 192, 256}: 192 exists because at M=5120 (1024 clips x 5 tokens) an N=2048 GEMM is 160 pair
 // tiles of 256x256 for 74 pairs (3 rounds, 72 % filled) but 220 tiles of 256x192 (3 rounds, 99 % filled, each
 // 25 % cheaper).
@@ -32,7 +33,7 @@ struct Tc2Cfg {
   static constexpr int kBRows = BN / 2;                    // this CTA's half of the W tile
   static constexpr int kBBytes = kBRows * kTcBK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kEpiBytes = 4 * 32 * kTcEpiStride * 4;
+  static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxStages = (kTcSmemLimit - 1024 - kEpiBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -70,6 +71,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kTcBK - 1) / kTcBK;
+  if (threadIdx.x == 0) { SDVG_TRACE(0); if (args.trace && blockIdx.x == 0) args.trace[40] = clock64(); }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -78,7 +80,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
-      ptx::mbar_init(&tempty_bar[b], 8);
+      ptx::mbar_init(&tempty_bar[b], 2 * kTcEpiWarps);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
@@ -97,8 +99,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   ptx::cluster_sync_all();  // peer barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SDVG_TRACE(1);
   pdl_wait();  // prologue above overlaps the previous kernel's tail (see common.cuh)
   pdl_trigger();
+  if (threadIdx.x == 0) SDVG_TRACE(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane per CTA)
@@ -119,6 +123,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
           ptx::tma_load_2d_cg2(sb, &tmB_hi, lead_full, kb * kTcBK, row_b);
           if (SPLIT) ptx::tma_load_2d_cg2(sb + Cfg::kBBytes, &tmB_lo, lead_full, kb * kTcBK, row_b);
+          if (t == pair && kb == 0) SDVG_TRACE(3);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -131,7 +136,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       uint32_t phase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
-      for (int t = pair; t < total_tiles; t += num_pairs) {
+      int tile_no = 0;
+      for (int t = pair; t < total_tiles; t += num_pairs, ++tile_no) {
         ptx::mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
@@ -139,6 +145,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
+          if (kb == 0 && tile_no < 8) SDVG_TRACE(8 + tile_no);
           const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
           const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
@@ -159,34 +166,44 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit_cg2_mc(&tfull_bar[buf], 0x3);
+        if (tile_no < 8) SDVG_TRACE(16 + tile_no);
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (own 128 rows)
+    // ------------------------------------------------------------------ epilogue warps (own 128 rows, 2 per quadrant)
     const int q = warp & 3;
-    float* stg = epi_stage + q * 32 * kTcEpiStride;
+    const int half = (warp - 2) >> 2;
+    constexpr int kChunks = BN / 32;
+    const int c_begin = half * (kChunks / 2), c_end = (half + 1) * (kChunks / 2);
+    float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int t = pair; t < total_tiles; t += num_pairs) {
+    int tile_no = 0;
+    for (int t = pair; t < total_tiles; t += num_pairs, ++tile_no) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0 && tile_no < 8) SDVG_TRACE(24 + tile_no);
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
       const uint32_t lead_tempty = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[buf]), 0);
       tc_epilogue_tile<BN, SPLIT, FANCY>(args, stg, tbase, m_blk * kTc2BM + static_cast<int>(rank) * kTcBM + q * 32,
-                                  n_blk * BN, lane, [lead_tempty]() { ptx::mbar_arrive_cluster(lead_tempty); });
+                                         n_blk * BN, lane, c_begin, c_end,
+                                         [lead_tempty]() { ptx::mbar_arrive_cluster(lead_tempty); });
+      if (warp == 2 && lane == 0 && tile_no < 8) SDVG_TRACE(32 + tile_no);
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SDVG_TRACE(4);
   ptx::cluster_sync_all();  // nobody leaves while the peer may still signal or read this CTA
   if (warp == 1) {
     __syncwarp();
     ptx::tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 0) { SDVG_TRACE(5); if (args.trace && blockIdx.x == 0) args.trace[41] = clock64(); }
 }
 
 template <int BN, bool SPLIT, bool FANCY>
