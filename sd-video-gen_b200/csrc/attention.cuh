@@ -18,6 +18,7 @@ constexpr int kAttnMaxS = 32;
 struct AttnArgs {
   const float* q; int ldq;
   const float* k; const float* v; int ldkv;
+  long long q_clip_stride, kv_clip_stride;  // elements between consecutive clips (0: Sq*ldq / Sk*ldkv, i.e. packed rows)
   int clips, heads, hd, Sq, Sk;
   int mask_kind; const float* mask;
   float scale;
@@ -54,9 +55,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   if (warp_global >= a.clips * a.heads) return;
   const int b = warp_global / a.heads, h = warp_global - b * a.heads;
   const int hd = a.hd;
-  const float* qb = a.q + static_cast<size_t>(b) * a.Sq * a.ldq + h * hd;
-  const float* kb = a.k + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
-  const float* vb = a.v + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
+  const float* qb = a.q + static_cast<size_t>(b) * a.q_clip_stride + h * hd;
+  const float* kb = a.k + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
+  const float* vb = a.v + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
   constexpr float kLog2e = 1.4426950408889634f;
 
   for (int i = a.q_first; i < a.Sq; ++i) {
@@ -149,9 +150,9 @@ __global__ void __launch_bounds__(128) attention_reg_kernel(const __grid_constan
   if (warp_global >= a.clips * a.heads) return;
   const int b = warp_global / a.heads, h = warp_global - b * a.heads;
   const int hd = a.hd;
-  const float* qb = a.q + static_cast<size_t>(b) * a.Sq * a.ldq + h * hd;
-  const float* kb = a.k + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
-  const float* vb = a.v + static_cast<size_t>(b) * a.Sk * a.ldkv + h * hd;
+  const float* qb = a.q + static_cast<size_t>(b) * a.q_clip_stride + h * hd;
+  const float* kb = a.k + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
+  const float* vb = a.v + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
   float kr[SMAX][EPL], vr[SMAX][EPL];
 #pragma unroll
   for (int j = 0; j < SMAX; ++j) {
@@ -249,9 +250,9 @@ __global__ void __launch_bounds__(128) attention_exact_kernel(const __grid_const
   if (warp_global >= a.clips * a.heads) return;
   const int b = warp_global / a.heads, h = warp_global - b * a.heads;
   constexpr int hd = 32 * EPL;
-  const float* qb = a.q + static_cast<size_t>(b) * SQ * a.ldq + h * hd;
-  const float* kb = a.k + static_cast<size_t>(b) * SK * a.ldkv + h * hd;
-  const float* vb = a.v + static_cast<size_t>(b) * SK * a.ldkv + h * hd;
+  const float* qb = a.q + static_cast<size_t>(b) * a.q_clip_stride + h * hd;
+  const float* kb = a.k + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
+  const float* vb = a.v + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
   float kr[SK][EPL], vr[SK][EPL];
 #pragma unroll
   for (int j = 0; j < SK; ++j) load_frag<VEC, NCH>(kr[j], kb + static_cast<size_t>(j) * a.ldkv, hd, lane);
@@ -346,11 +347,15 @@ inline cudaError_t launch_attention_reg(const AttnArgs& a, int grid, cudaStream_
   return cudaErrorNotSupported;
 }
 
-inline cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
+inline cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t stream) {
+  AttnArgs a = a_in;
+  if (a.q_clip_stride == 0) a.q_clip_stride = static_cast<long long>(a.Sq) * a.ldq;
+  if (a.kv_clip_stride == 0) a.kv_clip_stride = static_cast<long long>(a.Sk) * a.ldkv;
   if (a.Sk > kAttnMaxS || a.Sq > kAttnMaxS || a.hd > 256) return cudaErrorInvalidValue;
   const int warps = a.clips * a.heads;
   const int grid = ceil_div(warps, 4);
-  const bool al4 = (a.ldq % 4 == 0) && (a.ldkv % 4 == 0) && (a.ld32 % 4 == 0);
+  const bool al4 = (a.ldq % 4 == 0) && (a.ldkv % 4 == 0) && (a.ld32 % 4 == 0) && (a.q_clip_stride % 4 == 0) &&
+                   (a.kv_clip_stride % 4 == 0);
   cudaError_t fast = cudaErrorNotSupported;
   if (al4 && a.hd == 256) fast = launch_attention_exact<4, 2>(a, grid, stream);
   else if (al4 && a.hd == 128) fast = launch_attention_exact<4, 1>(a, grid, stream);

@@ -35,15 +35,27 @@ struct Epilogue {
   //   0 identity;  1 clip-major (b*S+s) -> sequence-major (s*B+b), the reference's (S,B,E) return layout
   //   (models/transformer.py:60-68);  2 only the last token of every clip is written, to row b
   //   (prediction/predict.py:42 keeps pred[:, -1]).
+  //   3 clip-strided: token (clip b, position s) -> row b*out_clip_rows + out_row_off + s (token-local caches
+  //   of the rollout, indexed by history slot)
   int row_map = 0;
   int clips = 0;
+  int out_clip_rows = 0, out_row_off = 0;
+  // residual read with the same clip-strided addressing when res_clip_rows > 0
+  int res_clip_rows = 0, res_row_off = 0;
 };
 
 __device__ __forceinline__ int epi_out_row(const Epilogue& e, int row) {
   if (e.row_map == 0) return row;
   const int b = row / e.rows_per_clip, s = row - b * e.rows_per_clip;
   if (e.row_map == 1) return s * e.clips + b;
+  if (e.row_map == 3) return b * e.out_clip_rows + e.out_row_off + s;
   return (s == e.rows_per_clip - 1) ? b : -1;
+}
+
+__device__ __forceinline__ int epi_res_row(const Epilogue& e, int row) {
+  if (e.res_clip_rows == 0) return row;
+  const int b = row / e.rows_per_clip, s = row - b * e.rows_per_clip;
+  return b * e.res_clip_rows + e.res_row_off + s;
 }
 
 // Row-dependent part resolved once per row: which PE row this token's clip uses (-1: none).
@@ -59,7 +71,7 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, float acc, int row
   v *= e.alpha;
   if (pe_row >= 0) v += __ldg(e.pe + static_cast<size_t>(pe_row) * e.ld_pe + col);
   if (e.relu) v = fmaxf(v, 0.0f);
-  if (e.residual) v += __ldg(e.residual + static_cast<size_t>(row) * e.ld_res + col);
+  if (e.residual) v += __ldg(e.residual + static_cast<size_t>(epi_res_row(e, row)) * e.ld_res + col);
   return v;
 }
 

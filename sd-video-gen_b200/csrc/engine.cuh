@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -98,6 +99,13 @@ class Engine {
   int max_rows = 0;
   ActBuf lat_s, lat_t, emb_s, emb_t, xs, xt, ybuf, qkv, attn, ffh, mem, qc, kvc, fin;
   float* hist = nullptr;     // rollout history [max_clips][max_history][E]
+  // token-local caches of the rollout, indexed by (clip, history slot): the embedding and the layer-0 Q/K/V of
+  // encoder and decoder self-attention depend on one token only (SURVEY.md fact 5 - the only K/V that can be
+  // cached exactly), so each is computed once, when a frame first enters a window
+  float* c_emb = nullptr;    // [max_clips * max_history][d]
+  float* c_qkv_e = nullptr;  // [max_clips * max_history][3d]
+  float* c_qkv_d = nullptr;  // [max_clips * max_history][3d]
+  bool use_cache = true;
   int* pe_mod64 = nullptr;   // [max_clips] b mod 64
 
   struct TimedSpan { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -335,9 +343,15 @@ class Engine {
     SDVG_ACT(kvc, 2 * d, true, false, false);
     SDVG_ACT(fin, d, S, T, sa);
 #undef SDVG_ACT
-    if (c.max_history > 0 &&
-        (e = dalloc(&hist, static_cast<size_t>(c.max_clips) * c.max_history * E)) != cudaSuccess)
-      return fail_cuda(e, "history alloc");
+    if (c.max_history > 0) {
+      const size_t slots_total = static_cast<size_t>(c.max_clips) * c.max_history;
+      if ((e = dalloc(&hist, slots_total * E)) != cudaSuccess) return fail_cuda(e, "history alloc");
+      if (const char* v = std::getenv("SDVG_CACHE")) use_cache = std::atoi(v) != 0;
+      if (use_cache && ((e = dalloc(&c_emb, slots_total * d)) != cudaSuccess ||
+                        (e = dalloc(&c_qkv_e, slots_total * 3 * d)) != cudaSuccess ||
+                        (e = dalloc(&c_qkv_d, slots_total * 3 * d)) != cudaSuccess))
+        return fail_cuda(e, "cache alloc");
+    }
     std::vector<int> mod(c.max_clips);
     for (int i = 0; i < c.max_clips; ++i) mod[i] = i % 64;
     if ((e = dalloc(&pe_mod64, static_cast<size_t>(c.max_clips))) != cudaSuccess) return fail_cuda(e, "pe alloc");
@@ -532,9 +546,11 @@ class Engine {
   }
 
   cudaError_t attention(const float* q, int ldq, const float* k, const float* v, int ldkv, int B, int Sq, int Sk,
-                        int mask_kind, const float* mask, int q_first, const ActBuf& dst, cudaStream_t st) {
+                        int mask_kind, const float* mask, int q_first, const ActBuf& dst, cudaStream_t st,
+                        long long q_clip_stride = 0, long long kv_clip_stride = 0) {
     AttnArgs a{};
     a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv;
+    a.q_clip_stride = q_clip_stride; a.kv_clip_stride = kv_clip_stride;
     a.clips = B; a.heads = cfg.num_heads; a.hd = cfg.dim_model / cfg.num_heads; a.Sq = Sq; a.Sk = Sk;
     a.mask_kind = mask_kind; a.mask = mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(a.hd));
@@ -572,8 +588,12 @@ class Engine {
 
   // One pass of the model on operand buffers lat_s (and lat_t unless `same`).  `oe` describes where the
   // output latents go (fp32 destination, row mapping).
+  // Token-local cache step of the rollout: lat_s holds only the `n_new` newest tokens of the window (the last
+  // n_new positions); cache rows of clip b are slots [b*Hn, (b+1)*Hn), the window starts at slot `first`.
+  struct CacheStep { int Hn, first, n_new; };
+
   cudaError_t run_model(int B, int Ss, int St, bool same, int mask_kind, const float* mask, const int* pe_index,
-                        Epilogue oe, cudaStream_t st) {
+                        Epilogue oe, cudaStream_t st, const CacheStep* cs = nullptr) {
     const int d = cfg.dim_model;
     const int Ms = B * Ss, Mt = B * St;
     const int Le = static_cast<int>(enc.size()), Ld = static_cast<int>(dec.size());
@@ -610,11 +630,44 @@ class Engine {
       return layernorm(ybuf, M, norm, chained, x_out, want_f32, S, 0, st);
     };
 
+    // layer-0 self-attention from the token-local caches (cs != nullptr): only the new tokens go through the
+    // embedding and the layer-0 QKV GEMMs; attention and the out-proj residual read the cached rows by slot
+    auto self_attention_cached = [&](float* c_qkv, const AttnWeights& w, int S, int M, int mk,
+                                     const LNParam& norm, const ActBuf& x_out) -> cudaError_t {
+      Epilogue e;  // new tokens' Q/K/V -> cache rows (clip b, slot first + S - n_new + j)
+      e.rows_per_clip = cs->n_new; e.row_map = 3; e.out_clip_rows = cs->Hn; e.out_row_off = cs->first + S - cs->n_new;
+      e.out32 = c_qkv; e.ld32 = 3 * d;
+      SDVG_CK(gemm(emb_s, w.qkv, B * cs->n_new, e, st));
+      const float* base = c_qkv + static_cast<size_t>(cs->first) * 3 * d;
+      const long long cstride = static_cast<long long>(cs->Hn) * 3 * d;
+      SDVG_CK(attention(base, 3 * d, base + d, base + 2 * d, 3 * d, B, S, S, mk, nullptr, 0, attn, st, cstride, cstride));
+      Epilogue eo;
+      eo.residual = c_emb; eo.ld_res = d; eo.rows_per_clip = S; eo.res_clip_rows = cs->Hn; eo.res_row_off = cs->first;
+      out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+      SDVG_CK(gemm(attn, w.out, M, eo, st));
+      return layernorm(ybuf, M, norm, nullptr, x_out, true, S, 0, st);
+    };
+
     // ---------------- encoder
-    SDVG_CK(embed(lat_s, Ss, emb_s));
+    if (cs) {
+      Epilogue e;  // embedding of the new tokens: fp32 -> cache rows, operand planes -> emb_s (packed new rows)
+      e.alpha = sqrt_d; e.pe = pe_table; e.ld_pe = d; e.pe_index = pe_index; e.rows_per_clip = cs->n_new;
+      e.row_map = 3; e.out_clip_rows = cs->Hn; e.out_row_off = cs->first + Ss - cs->n_new;
+      e.out32 = c_emb; e.ld32 = d;
+      e.out_hi = emb_s.p.hi; e.out_lo = emb_s.p.lo; e.ld16 = emb_s.p.ld;
+      if (!tc()) {
+        // SIMT mode has no planes: the QKV GEMMs read the new rows' fp32 embedding, so write them packed as well
+        Epilogue e2 = e; e2.row_map = 0; e2.out32 = emb_s.f32; e2.ld32 = emb_s.ld32;
+        SDVG_CK(gemm(lat_s, embedding, B * cs->n_new, e2, st));
+      }
+      SDVG_CK(gemm(lat_s, embedding, B * cs->n_new, e, st));
+    } else {
+      SDVG_CK(embed(lat_s, Ss, emb_s));
+    }
     const ActBuf* x = &emb_s;
     for (int l = 0; l < Le; ++l) {
-      SDVG_CK(self_attention(*x, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs));
+      if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_e, enc[l].sa, Ss, Ms, 0, enc[l].n1, xs));
+      else SDVG_CK(self_attention(*x, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs));
       const bool last = (l == Le - 1);
       SDVG_CK(ffn(xs, enc[l].ff1, enc[l].ff2, Ms, Ss, enc[l].n2, last ? &enc_norm : nullptr, last ? mem : xs, !last));
       x = &xs;
@@ -625,7 +678,8 @@ class Engine {
     const ActBuf* y = &emb_s;
     if (!same) { SDVG_CK(embed(lat_t, St, emb_t)); y = &emb_t; }
     for (int l = 0; l < Ld; ++l) {
-      SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt));
+      if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_d, dec[l].sa, St, Mt, mask_kind, dec[l].n1, xt));
+      else SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt));
       // cross attention: Q from the target stream, K/V from the encoder memory
       Epilogue eq;
       out_to(eq, qc, true); eq.out_hi = nullptr; eq.out_lo = nullptr;
@@ -704,6 +758,10 @@ class Engine {
       cudaError_t e = pack(a, st);
       if (e != cudaSuccess) return fail_cuda(e, "context ingest");
     }
+    // exact token-local caches: plain sliding window only (the predict.py-faithful sequence has an SOS frame and
+    // drops a real frame, so its windows are not contiguous slots), causal mask, at least one layer on each side
+    const bool cached = use_cache && c_emb && !faithful && !enc.empty() && !dec.empty();
+    int cached_upto = 0;  // history slots [.., cached_upto) already have cache rows
     std::vector<int> seq;
     for (int t = 0; t < n_pred; ++t) {
       seq.clear();
@@ -719,11 +777,19 @@ class Engine {
         for (int i = have - W; i < have; ++i) seq.push_back(i);
       }
       const int S = static_cast<int>(seq.size());
-      cudaError_t e = ingest(hist, hstride, E, seq.data(), B, S, 1.0f, lat_s, st);
+      CacheStep cstep{Hn, seq[0], 0};
+      if (cached) {
+        const int have = C + t;
+        const int from = seq[0] > cached_upto ? seq[0] : cached_upto;
+        cstep.n_new = have - from;
+        cached_upto = have;
+      }
+      cudaError_t e = cached ? ingest(hist, hstride, E, seq.data() + (S - cstep.n_new), B, cstep.n_new, 1.0f, lat_s, st)
+                             : ingest(hist, hstride, E, seq.data(), B, S, 1.0f, lat_s, st);
       if (e != cudaSuccess) return fail_cuda(e, "window gather");
       Epilogue oe;  // last position of every clip -> history slot C+t          predict.py:42
       oe.out32 = hist + static_cast<size_t>(C + t) * E; oe.ld32 = static_cast<int>(hstride); oe.row_map = 2;
-      e = run_model(B, S, S, true, 1, nullptr, pe, oe, st);
+      e = run_model(B, S, S, true, 1, nullptr, pe, oe, st, cached ? &cstep : nullptr);
       if (e != cudaSuccess) return fail_cuda(e, "rollout step");
       if (teacher) {
         // export this prediction, then overwrite the slot with the teacher frame

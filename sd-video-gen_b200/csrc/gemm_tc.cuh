@@ -166,7 +166,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + lr;
-          res_n[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(residual + static_cast<size_t>(row0 + rr) * ld_res + col))
+          size_t rrow = static_cast<size_t>(row0 + rr);
+          if constexpr (FANCY) rrow = static_cast<size_t>(epi_res_row(e, row0 + rr));
+          res_n[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(residual + rrow * ld_res + col))
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -222,6 +224,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
               }
               if (e.row_map == 1) out_row = sidx * e.clips + b;
               else if (e.row_map == 2) out_row = (sidx == e.rows_per_clip - 1) ? b : -1;
+              else if (e.row_map == 3) out_row = b * e.out_clip_rows + e.out_row_off + sidx;
             }
           }
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -241,7 +244,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
 }
 
 // The embedding / output projections are the only GEMMs that scale, add positional rows or remap output rows.
-inline bool epilogue_is_fancy(const Epilogue& e) { return e.alpha != 1.0f || e.pe != nullptr || e.row_map != 0; }
+inline bool epilogue_is_fancy(const Epilogue& e) {
+  return e.alpha != 1.0f || e.pe != nullptr || e.row_map != 0 || e.res_clip_rows != 0;
+}
 
 template <int BN, bool SPLIT, bool FANCY>
 __global__ void __launch_bounds__(kTcThreads, 1)

@@ -173,3 +173,24 @@ def test_bench_size_batch_properties():
     assert R.max_rel_per_frame(out[:8].cpu(), g["free5"][:, :2]).max() < TOL32
     shard = sdvg_b200.rollout(m, ctx[512:640], 2, 5, pe_index=sdvg_b200.pe_index_for(512, 640))
     assert R.max_rel_per_frame(shard.cpu(), out[512:640].cpu()).max() < 1e-5
+
+
+def test_token_local_cache_is_exact(monkeypatch):
+    """The rollout computes the embedding and the layer-0 Q/K/V of each frame once (token-local caches, the only
+    exact K/V reuse this model allows - SURVEY.md fact 5).  Same results as recomputing the whole window."""
+    g = load_golden("small_rollout")
+    ctx = torch.randn(70, 7, 256, generator=torch.Generator().manual_seed(8)).to(DEV)
+    teacher = torch.randn(70, 5, 256, generator=torch.Generator().manual_seed(9)).to(DEV)
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SDVG_CACHE", flag)          # read when the handle is created
+        for prec in ("fp32", "mixed"):
+            m, _ = ours_from(g, prec)
+            outs[flag, prec, "free"] = sdvg_b200.rollout(m, ctx, 5, 5)
+            outs[flag, prec, "w3"] = sdvg_b200.rollout(m, ctx, 5, 3)
+            outs[flag, prec, "grow"] = sdvg_b200.rollout(m, ctx[:, :2], 5, 6)      # window grows from 2 to 6 tokens
+            outs[flag, prec, "tf"] = sdvg_b200.rollout(m, ctx, 5, 5, teacher=teacher)
+    for (flag, prec, kind), v in outs.items():
+        if flag == "1":
+            ref = outs["0", prec, kind]
+            assert R.max_rel_per_frame(v.cpu(), ref.cpu()).max() < 1e-6, (prec, kind)
