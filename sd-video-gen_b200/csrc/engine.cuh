@@ -519,7 +519,7 @@ class Engine {
     }
     const bool split = L.split && A.p.lo != nullptr;
     const TilePlan plan = choose_plan(M, L.N, split);
-    TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, nullptr, e};
+    TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, 0, nullptr, e};
     const double planes = split ? 2.0 : 1.0;
     Scope sc(this, KC_GEMM_TC, flops, 2.0 * planes * (double(M) * L.K + double(L.N) * L.K) + 4.0 * double(M) * L.N, st);
     return gemm_tc_dispatch(A.p, L.p, split, plan, args, st);

@@ -63,6 +63,7 @@ struct TcGemmArgs {
   int M, N, K;
   int bf16;  // operand format of the hi planes
   int vec4;  // all epilogue pointers / pitches are 16-byte aligned and N % 4 == 0 (set by the launcher)
+  int max_stages;             // 0 = all smem stages; >0 caps the TMA ring depth (pipeline experiments, SDVG_STAGES)
   unsigned long long* trace;  // optional [64] device buffer: CTA 0 records %globaltimer at pipeline events (tools/gemm_trace.py)
   Epilogue epi;
 };
@@ -265,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform (see gemm_tc2.cuh)
   const int lane = threadIdx.x & 31;
   const int M = args.M, N = args.N, K = args.K;
   const int m_tiles = (M + kTcBM - 1) / kTcBM;
@@ -303,47 +304,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   pdl_trigger();
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
+        uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           ptx::tma_load_2d(sp, &tmA_hi, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
           if (SPLIT) ptx::tma_load_2d(sp + Cfg::kABytes, &tmA_lo, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
-          uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
           ptx::tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kTcBK, n_blk * BN);
           if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &tmB_lo, &full_bar[stage], kb * kTcBK, n_blk * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_f16(kTcBM, BN, args.bf16 != 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int buf = 0;
-      uint32_t buf_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        ptx::mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    const uint32_t idesc = ptx::make_idesc_f16(kTcBM, BN, args.bf16 != 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
+      const uint32_t d1 = d0 + BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
-        const uint32_t d1 = d0 + BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
-          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
-          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(sb);
-          const uint64_t a_lo = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
-          const uint64_t b_lo = ptx::make_kmajor_sw128_desc(sb + Cfg::kBBytes);
+        const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
+        const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
+        const uint64_t b_hi = ptx::make_kmajor_sw128_desc(sb);
+        const uint64_t a_lo = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
+        const uint64_t b_lo = ptx::make_kmajor_sw128_desc(sb + Cfg::kBBytes);
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kTcBK / 16; ++k) {
             const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
@@ -354,12 +356,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               ptx::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          ptx::umma_commit(&empty_bar[stage]);                         // smem stage reusable once these MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[buf]);     // accumulator(s) of this tile complete
         }
-        ptx::umma_commit(&tfull_bar[buf]);  // accumulator(s) of this tile complete
-        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (2 per 32-lane TMEM quadrant)

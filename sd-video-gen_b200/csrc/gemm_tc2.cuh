@@ -62,15 +62,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] used in the leader: both epilogues -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index / cluster rank as provably warp-uniform values: the producer and MMA roles run with the whole
+  // warp converged and elect one lane per instruction, so that TMA / tcgen05 operands live in uniform registers.
+  // (With `if (lane == 0)` around the role loops ptxas wrapped every UTMALDG / UTCHMMA / UTCBAR in an
+  // ELECT + R2UR.BROADCAST + BRA.U.ANY loop: ~540 cycles per K block regardless of tile width.)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int M = args.M, N = args.N, K = args.K;
   const int m_tiles = (M + kTc2BM - 1) / kTc2BM;
   const int n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kTcBK - 1) / kTcBK;
+  const int nstages = (args.max_stages > 0 && args.max_stages < Cfg::kStages) ? args.max_stages : Cfg::kStages;
   if (threadIdx.x == 0) { SDVG_TRACE(0); if (args.trace && blockIdx.x == 0) args.trace[40] = clock64(); }
 
   if (threadIdx.x == 0) {
@@ -105,32 +110,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (threadIdx.x == 0) SDVG_TRACE(2);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane per CTA)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = pair; t < total_tiles; t += num_pairs) {
-        const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
-        const int row_a = m_blk * kTc2BM + static_cast<int>(rank) * kTcBM;
-        const int row_b = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
-          const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < total_tiles; t += num_pairs) {
+      const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
+      const int row_a = m_blk * kTc2BM + static_cast<int>(rank) * kTcBM;
+      const int row_b = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
+        uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
+        const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx_cluster(lead_full, Cfg::kStageBytes);
           ptx::tma_load_2d_cg2(sp, &tmA_hi, lead_full, kb * kTcBK, row_a);
           if (SPLIT) ptx::tma_load_2d_cg2(sp + Cfg::kABytes, &tmA_lo, lead_full, kb * kTcBK, row_a);
-          uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
           ptx::tma_load_2d_cg2(sb, &tmB_hi, lead_full, kb * kTcBK, row_b);
           if (SPLIT) ptx::tma_load_2d_cg2(sb + Cfg::kBBytes, &tmB_lo, lead_full, kb * kTcBK, row_b);
-          if (t == pair && kb == 0) SDVG_TRACE(3);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (t == pair && kb == 0 && lane == 0) SDVG_TRACE(3);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA, one lane)
-    if (rank == 0 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, one elected lane issues)
+    if (rank == 0) {
       const uint32_t idesc = ptx::make_idesc_f16(kTc2BM, BN, args.bf16 != 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -145,28 +151,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          if (kb == 0 && tile_no < 8) SDVG_TRACE(8 + tile_no);
+          if (kb == 0 && tile_no < 8 && lane == 0) SDVG_TRACE(8 + tile_no);
           const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
           const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
           const uint64_t b_hi = ptx::make_kmajor_sw128_desc(sb);
           const uint64_t a_lo = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
           const uint64_t b_lo = ptx::make_kmajor_sw128_desc(sb + Cfg::kBBytes);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kTcBK / 16; ++k) {
-            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-            const uint64_t adv = static_cast<uint64_t>(k * 2);
-            ptx::umma_f16_cg2(d0, a_hi + adv, b_hi + adv, idesc, acc);
-            if (SPLIT) {
-              ptx::umma_f16_cg2(d1, a_hi + adv, b_lo + adv, idesc, acc);
-              ptx::umma_f16_cg2(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+            for (int k = 0; k < kTcBK / 16; ++k) {
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              const uint64_t adv = static_cast<uint64_t>(k * 2);
+              ptx::umma_f16_cg2(d0, a_hi + adv, b_hi + adv, idesc, acc);
+              if (SPLIT) {
+                ptx::umma_f16_cg2(d1, a_hi + adv, b_lo + adv, idesc, acc);
+                ptx::umma_f16_cg2(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
             }
+            ptx::umma_commit_cg2_mc(&empty_bar[stage], 0x3);
+            if (kb == num_kb - 1) ptx::umma_commit_cg2_mc(&tfull_bar[buf], 0x3);
           }
-          ptx::umma_commit_cg2_mc(&empty_bar[stage], 0x3);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit_cg2_mc(&tfull_bar[buf], 0x3);
-        if (tile_no < 8) SDVG_TRACE(16 + tile_no);
+        if (tile_no < 8 && lane == 0) SDVG_TRACE(16 + tile_no);
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
     }
