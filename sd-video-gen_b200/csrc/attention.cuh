@@ -347,6 +347,155 @@ inline cudaError_t launch_attention_reg(const AttnArgs& a, int grid, cudaStream_
   return cudaErrorNotSupported;
 }
 
+// 16-bit-input variant (fp16 / bf16 Q, K, V written by the projection GEMM's epilogue as operand planes): used by
+// the 16-bit precision modes for every attention except layer 0, whose un-normalised inputs need fp32 scores
+// (SURVEY.md fact 6).  Halves the bytes of the bandwidth-bound attention kernels and of the QKV epilogue stores;
+// measured effect on the C1 golden rollout: 8.3e-4 -> 1.05e-3 per-frame max-rel (oracle emulation), bar 5e-3.
+// Lane l owns head elements [l*VEC, (l+1)*VEC): one 16-byte load per row at hd = 256.
+template <int VEC>
+__device__ __forceinline__ void load_frag16(float (&f)[VEC], const uint16_t* __restrict__ row, int lane, int bf16) {
+  const uint16_t* p = row + lane * VEC;
+  uint32_t w[(VEC + 1) / 2];
+  if constexpr (VEC == 8) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  } else if constexpr (VEC == 4) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    w[0] = t.x; w[1] = t.y;
+  } else if constexpr (VEC == 2) {
+    w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+  } else {
+    w[0] = __ldg(p);
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const uint16_t h = static_cast<uint16_t>(i & 1 ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu));
+    f[i] = bf16 ? __bfloat162float(__ushort_as_bfloat16(h)) : __half2float(__ushort_as_half(h));
+  }
+}
+
+template <int VEC, int SQ, int SK, int MASK>
+__global__ void __launch_bounds__(128) attention_exact16_kernel(const __grid_constant__ AttnArgs a) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr int hd = 32 * VEC;
+  pdl_wait();
+  pdl_trigger();
+  const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= a.clips * a.heads) return;
+  const int b = warp_global / a.heads, h = warp_global - b * a.heads;
+  const uint16_t* qb = reinterpret_cast<const uint16_t*>(a.q) + static_cast<size_t>(b) * a.q_clip_stride + h * hd;
+  const uint16_t* kb = reinterpret_cast<const uint16_t*>(a.k) + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
+  const uint16_t* vb = reinterpret_cast<const uint16_t*>(a.v) + static_cast<size_t>(b) * a.kv_clip_stride + h * hd;
+  float kr[SK][VEC], vr[SK][VEC];
+#pragma unroll
+  for (int j = 0; j < SK; ++j) load_frag16<VEC>(kr[j], kb + static_cast<size_t>(j) * a.ldkv, lane, a.bf16);
+#pragma unroll
+  for (int j = 0; j < SK; ++j) load_frag16<VEC>(vr[j], vb + static_cast<size_t>(j) * a.ldkv, lane, a.bf16);
+  const float scale2 = a.scale * kLog2e;
+#pragma unroll 1
+  for (int i = a.q_first; i < SQ; ++i) {
+    float ql[VEC];
+    load_frag16<VEC>(ql, qb + static_cast<size_t>(i) * a.ldq, lane, a.bf16);
+    float sc[SK];
+#pragma unroll
+    for (int j = 0; j < SK; ++j) {
+      float part = 0.f;
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) part = fmaf(ql[t], kr[j][t], part);
+      sc[j] = part;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < SK; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SK; ++j) {
+      float sv = sc[j] * scale2;
+      if (MASK == 1 && j > i + (SK - SQ)) sv = -INFINITY;
+      sc[j] = sv;
+      mx = fmaxf(mx, sv);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SK; ++j) { sc[j] = exp2f(sc[j] - mx); sum += sc[j]; }
+    const float inv = 1.0f / sum;
+    float ol[VEC];
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) ol[t] = 0.f;
+#pragma unroll
+    for (int j = 0; j < SK; ++j) {
+      const float pj = sc[j] * inv;
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) ol[t] = fmaf(pj, vr[j][t], ol[t]);
+    }
+    const size_t row = static_cast<size_t>(b) * SQ + i;
+    const int col = h * hd + lane * VEC;
+    if (a.out32) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) a.out32[row * a.ld32 + col + v] = ol[v];
+    }
+    if (a.out_hi) {
+      uint16_t hi[VEC], lo[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { hi[v] = to_plane_hi(ol[v], a.bf16); lo[v] = to_plane_lo(ol[v], hi[v]); }
+      if constexpr (VEC == 8) {
+        *reinterpret_cast<uint4*>(a.out_hi + row * a.ld16 + col) =
+            make_uint4(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16), hi[4] | (uint32_t(hi[5]) << 16), hi[6] | (uint32_t(hi[7]) << 16));
+        if (a.out_lo)
+          *reinterpret_cast<uint4*>(a.out_lo + row * a.ld16 + col) =
+              make_uint4(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16), lo[4] | (uint32_t(lo[5]) << 16), lo[6] | (uint32_t(lo[7]) << 16));
+      } else if constexpr (VEC == 4) {
+        *reinterpret_cast<uint2*>(a.out_hi + row * a.ld16 + col) = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+        if (a.out_lo) *reinterpret_cast<uint2*>(a.out_lo + row * a.ld16 + col) = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+      } else if constexpr (VEC == 2) {
+        *reinterpret_cast<uint32_t*>(a.out_hi + row * a.ld16 + col) = hi[0] | (uint32_t(hi[1]) << 16);
+        if (a.out_lo) *reinterpret_cast<uint32_t*>(a.out_lo + row * a.ld16 + col) = lo[0] | (uint32_t(lo[1]) << 16);
+      } else {
+        a.out_hi[row * a.ld16 + col] = hi[0];
+        if (a.out_lo) a.out_lo[row * a.ld16 + col] = lo[0];
+      }
+    }
+  }
+}
+
+// shapes the 16-bit-input kernel is instantiated for (the engine asks before choosing the 16-bit Q/K/V layout)
+inline bool attention16_supported(int hd, int Sq, int Sk, int mask_kind) {
+  const bool shape = (Sq == 5 && Sk == 5) || (Sq == 6 && Sk == 6) || (Sq == 10 && Sk == 10) || (Sq == 5 && Sk == 6);
+  return shape && (hd == 256 || hd == 128 || hd == 64 || hd == 32) && (mask_kind == 0 || mask_kind == 1);
+}
+
+template <int VEC, int SQ, int SK>
+inline cudaError_t launch_attention16_m(const AttnArgs& a, int grid, cudaStream_t stream) {
+  if (a.mask_kind == 0) return launch_kernel(attention_exact16_kernel<VEC, SQ, SK, 0>, dim3(grid), dim3(128), 0, stream, a);
+  return launch_kernel(attention_exact16_kernel<VEC, SQ, SK, 1>, dim3(grid), dim3(128), 0, stream, a);
+}
+template <int VEC>
+inline cudaError_t launch_attention16_v(const AttnArgs& a, int grid, cudaStream_t stream) {
+  if (a.Sq == 5 && a.Sk == 5) return launch_attention16_m<VEC, 5, 5>(a, grid, stream);
+  if (a.Sq == 6 && a.Sk == 6) return launch_attention16_m<VEC, 6, 6>(a, grid, stream);
+  if (a.Sq == 10 && a.Sk == 10) return launch_attention16_m<VEC, 10, 10>(a, grid, stream);
+  return launch_attention16_m<VEC, 5, 6>(a, grid, stream);
+}
+// Q/K/V given as 16-bit planes (a.q/a.k/a.v point at uint16 data; ldq/ldkv/clip strides in elements).
+inline cudaError_t launch_attention16(const AttnArgs& a_in, cudaStream_t stream) {
+  AttnArgs a = a_in;
+  if (a.q_clip_stride == 0) a.q_clip_stride = static_cast<long long>(a.Sq) * a.ldq;
+  if (a.kv_clip_stride == 0) a.kv_clip_stride = static_cast<long long>(a.Sk) * a.ldkv;
+  if (!attention16_supported(a.hd, a.Sq, a.Sk, a.mask_kind) || a.ldq % 8 || a.ldkv % 8 || a.q_clip_stride % 8 ||
+      a.kv_clip_stride % 8)
+    return cudaErrorInvalidValue;
+  const int grid = ceil_div(a.clips * a.heads, 4);
+  switch (a.hd) {
+    case 256: return launch_attention16_v<8>(a, grid, stream);
+    case 128: return launch_attention16_v<4>(a, grid, stream);
+    case 64: return launch_attention16_v<2>(a, grid, stream);
+    default: return launch_attention16_v<1>(a, grid, stream);
+  }
+}
+
 inline cudaError_t launch_attention(const AttnArgs& a_in, cudaStream_t stream) {
   AttnArgs a = a_in;
   if (a.q_clip_stride == 0) a.q_clip_stride = static_cast<long long>(a.Sq) * a.ldq;

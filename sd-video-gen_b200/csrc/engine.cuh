@@ -98,6 +98,9 @@ class Engine {
 
   int max_rows = 0;
   ActBuf lat_s, lat_t, emb_s, emb_t, xs, xt, ybuf, qkv, attn, ffh, mem, qc, kvc, fin;
+  uint16_t* qkv16 = nullptr;  // [max_rows][3d] 16-bit Q|K|V of layers >= 1 (16-bit precision modes)
+  uint16_t* qc16 = nullptr;   // [max_rows][d]   cross-attention Q
+  uint16_t* kvc16 = nullptr;  // [max_rows][2d]  cross-attention K|V
   float* hist = nullptr;     // rollout history [max_clips][max_history][E]
   // token-local caches of the rollout, indexed by (clip, history slot): the embedding and the layer-0 Q/K/V of
   // encoder and decoder self-attention depend on one token only (SURVEY.md fact 5 - the only K/V that can be
@@ -119,6 +122,10 @@ class Engine {
   bool bf16() const { return cfg.precision == SDVG_BF16; }
   bool split_all() const { return cfg.precision == SDVG_FP32; }
   bool split_first() const { return cfg.precision == SDVG_FP32 || cfg.precision == SDVG_MIXED; }
+  // 16-bit modes keep Q/K/V of every attention except layer 0 as 16-bit planes (see attention.cuh)
+  bool qkv16_mode() const {
+    return cfg.precision == SDVG_FP16 || cfg.precision == SDVG_BF16 || cfg.precision == SDVG_MIXED;
+  }
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -343,6 +350,12 @@ class Engine {
     SDVG_ACT(kvc, 2 * d, true, false, false);
     SDVG_ACT(fin, d, S, T, sa);
 #undef SDVG_ACT
+    if (qkv16_mode()) {
+      if ((e = dalloc(&qkv16, static_cast<size_t>(max_rows) * 3 * d)) != cudaSuccess ||
+          (e = dalloc(&qc16, static_cast<size_t>(max_rows) * d)) != cudaSuccess ||
+          (e = dalloc(&kvc16, static_cast<size_t>(max_rows) * 2 * d)) != cudaSuccess)
+        return fail_cuda(e, "workspace alloc qkv16");
+    }
     if (c.max_history > 0) {
       const size_t slots_total = static_cast<size_t>(c.max_clips) * c.max_history;
       if ((e = dalloc(&hist, slots_total * E)) != cudaSuccess) return fail_cuda(e, "history alloc");
@@ -547,7 +560,7 @@ class Engine {
 
   cudaError_t attention(const float* q, int ldq, const float* k, const float* v, int ldkv, int B, int Sq, int Sk,
                         int mask_kind, const float* mask, int q_first, const ActBuf& dst, cudaStream_t st,
-                        long long q_clip_stride = 0, long long kv_clip_stride = 0) {
+                        long long q_clip_stride = 0, long long kv_clip_stride = 0, bool in16 = false) {
     AttnArgs a{};
     a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv;
     a.q_clip_stride = q_clip_stride; a.kv_clip_stride = kv_clip_stride;
@@ -559,8 +572,8 @@ class Engine {
     a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
     const double d = cfg.dim_model;
     Scope sc(this, KC_ATTN, 0.0,
-             double(B) * d * (4.0 * (Sq + 2.0 * Sk) + Sq * ((a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0))), st);
-    return launch_attention(a, st);
+             double(B) * d * ((in16 ? 2.0 : 4.0) * (Sq + 2.0 * Sk) + Sq * ((a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0))), st);
+    return in16 ? launch_attention16(a, st) : launch_attention(a, st);
   }
 
   cudaError_t pack(const PackArgs& a, cudaStream_t st) {
@@ -605,12 +618,21 @@ class Engine {
       out_to(e, dst, true);
       return gemm(lat, embedding, B * S, e, st);
     };
+    const int hd = d / cfg.num_heads;
     auto self_attention = [&](const ActBuf& x, const AttnWeights& w, int S, int M, int mk, const float* mptr,
-                              const LNParam& norm, const ActBuf& x_out) -> cudaError_t {
+                              const LNParam& norm, const ActBuf& x_out, bool first_layer) -> cudaError_t {
       Epilogue e;
-      out_to(e, qkv, true); e.out_hi = nullptr; e.out_lo = nullptr;
-      SDVG_CK(gemm(x, w.qkv, M, e, st));
-      SDVG_CK(attention(qkv.f32, 3 * d, qkv.f32 + d, qkv.f32 + 2 * d, 3 * d, B, S, S, mk, mptr, 0, attn, st));
+      if (qkv16 && !first_layer && attention16_supported(hd, S, S, mk)) {
+        e.out_hi = qkv16; e.ld16 = 3 * d;   // Q|K|V straight to 16-bit planes
+        SDVG_CK(gemm(x, w.qkv, M, e, st));
+        const float* q16 = reinterpret_cast<const float*>(qkv16);
+        SDVG_CK(attention(q16, 3 * d, reinterpret_cast<const float*>(qkv16 + d), reinterpret_cast<const float*>(qkv16 + 2 * d),
+                          3 * d, B, S, S, mk, nullptr, 0, attn, st, 0, 0, true));
+      } else {
+        out_to(e, qkv, true); e.out_hi = nullptr; e.out_lo = nullptr;
+        SDVG_CK(gemm(x, w.qkv, M, e, st));
+        SDVG_CK(attention(qkv.f32, 3 * d, qkv.f32 + d, qkv.f32 + 2 * d, 3 * d, B, S, S, mk, mptr, 0, attn, st));
+      }
       Epilogue eo;
       eo.residual = x.f32; eo.ld_res = x.ld32;
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
@@ -667,7 +689,7 @@ class Engine {
     const ActBuf* x = &emb_s;
     for (int l = 0; l < Le; ++l) {
       if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_e, enc[l].sa, Ss, Ms, 0, enc[l].n1, xs));
-      else SDVG_CK(self_attention(*x, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs));
+      else SDVG_CK(self_attention(*x, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs, l == 0));
       const bool last = (l == Le - 1);
       SDVG_CK(ffn(xs, enc[l].ff1, enc[l].ff2, Ms, Ss, enc[l].n2, last ? &enc_norm : nullptr, last ? mem : xs, !last));
       x = &xs;
@@ -679,15 +701,23 @@ class Engine {
     if (!same) { SDVG_CK(embed(lat_t, St, emb_t)); y = &emb_t; }
     for (int l = 0; l < Ld; ++l) {
       if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_d, dec[l].sa, St, Mt, mask_kind, dec[l].n1, xt));
-      else SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt));
+      else SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt, l == 0));
       // cross attention: Q from the target stream, K/V from the encoder memory
-      Epilogue eq;
-      out_to(eq, qc, true); eq.out_hi = nullptr; eq.out_lo = nullptr;
-      SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
-      Epilogue ekv;
-      out_to(ekv, kvc, true); ekv.out_hi = nullptr; ekv.out_lo = nullptr;
-      SDVG_CK(gemm(mem, dec[l].ca.kv, Ms, ekv, st));
-      SDVG_CK(attention(qc.f32, d, kvc.f32, kvc.f32 + d, 2 * d, B, St, Ss, 0, nullptr, 0, attn, st));
+      Epilogue eq, ekv;
+      if (qkv16 && attention16_supported(hd, St, Ss, 0)) {
+        eq.out_hi = qc16; eq.ld16 = d;
+        SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
+        ekv.out_hi = kvc16; ekv.ld16 = 2 * d;
+        SDVG_CK(gemm(mem, dec[l].ca.kv, Ms, ekv, st));
+        SDVG_CK(attention(reinterpret_cast<const float*>(qc16), d, reinterpret_cast<const float*>(kvc16),
+                          reinterpret_cast<const float*>(kvc16 + d), 2 * d, B, St, Ss, 0, nullptr, 0, attn, st, 0, 0, true));
+      } else {
+        out_to(eq, qc, true); eq.out_hi = nullptr; eq.out_lo = nullptr;
+        SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
+        out_to(ekv, kvc, true); ekv.out_hi = nullptr; ekv.out_lo = nullptr;
+        SDVG_CK(gemm(mem, dec[l].ca.kv, Ms, ekv, st));
+        SDVG_CK(attention(qc.f32, d, kvc.f32, kvc.f32 + d, 2 * d, B, St, Ss, 0, nullptr, 0, attn, st));
+      }
       Epilogue eo;
       eo.residual = xt.f32; eo.ld_res = xt.ld32;
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
