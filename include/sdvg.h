@@ -112,17 +112,22 @@ int sdvg_forward(sdvg_handle* h, const float* src, const float* tgt, int32_t B, 
  *   Every step runs the model on src = tgt = window with the causal mask and keeps the last position
  *   (predict.py:24-26,42), then slides the window over [context, predictions].
  *   window   : tokens per step (the reference hard-codes 5, predict.py:196); clipped to the history length.
- *   faithful : 0 = plain sliding window.  1 = the literal predict.py sequence: requires C == 5; first window is
- *              [SOS, f1..f5] with SOS = 2.0 (predict.py:124-130, utils/sd_utils.py:31,151-153), later windows
- *              are the last 5 of [f1..f4, p1..pk] (predict.py:193-196 drops the last real frame).
+ *   flags    : bit 0 (SDVG_ROLLOUT_FAITHFUL) = the literal predict.py sequence instead of a plain sliding window:
+ *              requires C == 5; first window is [SOS, f1..f5] with SOS = 2.0 (predict.py:124-130,
+ *              utils/sd_utils.py:31,151-153), later windows are the last 5 of [f1..f4, p1..pk] (predict.py:193-196
+ *              drops the last real frame).
+ *              bit 1 (SDVG_ROLLOUT_RESIDUAL) = the predict_diff.py variant: every prediction is the model output
+ *              plus the second-to-last frame of its window (prediction/predict_diff.py:33).
  *   teacher  : NULL, or (B, n_pred, E) device fp32 frames fed back instead of the model's own predictions
  *              (teacher forcing, used by the parity tests for reduced-precision modes).
  *   pe_index : (B) device int32 or NULL (NULL -> b mod 64, i.e. the reference run in chunks of 64 clips).
  *   scale_in / scale_out : multiply the context on ingest / the predictions on egress (0.18215 and 1/0.18215
  *              are the VAE latent scale of utils/sd_utils.py:143,159; 1.0 when the caller's latents are
  *              already scaled).  The fed-back frames are never rescaled. */
+#define SDVG_ROLLOUT_FAITHFUL 1
+#define SDVG_ROLLOUT_RESIDUAL 2
 int sdvg_rollout(sdvg_handle* h, const float* ctx, int32_t B, int32_t C, int32_t n_pred, int32_t window,
-                 int32_t faithful, const float* teacher, const int32_t* pe_index, float scale_in, float scale_out,
+                 int32_t flags, const float* teacher, const int32_t* pe_index, float scale_in, float scale_out,
                  float* out, void* stream);
 
 /* Per-kernel-class device timing (CUDA events around every launch of the library's kernels).  Off by default.

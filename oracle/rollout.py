@@ -26,12 +26,18 @@ def predict_ref(model, window):
         return pred[:, -1]
 
 
-def rollout_ref(model, ctx, n_pred, window, teacher=None):
-    """ctx (B,C,E) -> (B,n_pred,E).  ``teacher`` (B,n_pred,E): feed these instead of own predictions."""
+def predict_diff_ref(model, window):
+    """prediction/predict_diff.py:14-41 for all clips: last-position output + second-to-last input frame (:33)."""
+    return predict_ref(model, window) + window[:, -2]
+
+
+def rollout_ref(model, ctx, n_pred, window, teacher=None, residual=False):
+    """ctx (B,C,E) -> (B,n_pred,E).  ``teacher`` (B,n_pred,E): feed these instead of own predictions.
+    ``residual``: the predict_diff.py variant of ``predict``."""
     allx, outs = ctx, []
     X = allx[:, -window:]
     for t in range(n_pred):
-        p = predict_ref(model, X)
+        p = predict_diff_ref(model, X) if residual else predict_ref(model, X)
         outs.append(p)
         nxt = p if teacher is None else teacher[:, t]
         allx = torch.cat([allx, nxt[:, None]], 1)
@@ -39,15 +45,16 @@ def rollout_ref(model, ctx, n_pred, window, teacher=None):
     return torch.stack(outs, 1)
 
 
-def rollout_faithful(model, frames, n_pred):
-    """frames (B,5,E) real latents. Reproduces prediction/predict.py:117-197 (any B<=64; reference B=1)."""
+def rollout_faithful(model, frames, n_pred, residual=False):
+    """frames (B,5,E) real latents. Reproduces prediction/predict.py:117-197 (any B<=64; reference B=1);
+    ``residual`` = the same loop in prediction/predict_diff.py:117-192."""
     B, T, E = frames.shape
     sos = torch.full((B, 1, E), SOS_VALUE, dtype=frames.dtype)
     X = torch.cat([sos, frames], 1)              # use_sos=True, predict.py:124
     inputs = frames                               # predict.py:136-141 (all frames except SOS)
     preds = []
     for _ in range(n_pred):
-        p = predict_ref(model, X)                 # predict.py:144
+        p = predict_diff_ref(model, X) if residual else predict_ref(model, X)   # predict.py:144 / predict_diff.py:140
         preds.append(p)
         all_latents = torch.cat([inputs[:, :-1], torch.stack(preds, 1)], 1)   # predict.py:193
         X = all_latents[:, -5:]                   # predict.py:196

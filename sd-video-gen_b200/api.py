@@ -3,10 +3,12 @@ from . import _lib
 from .config import CONFIGS, latent_dim, parse_config_args
 from .dist import pe_index_for, rollout_sharded, shard_bounds
 from .positional_encoding import PositionalEncoding
-from .predict import LATENT_SCALE, SOS_VALUE, HostRollout, predict, rollout, rollout_from_host
-from .transformer import Transformer
+from .predict import (LATENT_SCALE, SOS_VALUE, HostRollout, predict, predict_diff, predict_future, rollout,
+                      rollout_from_host)
+from .transformer import Identity, Transformer, TransformerFuture
 
-__all__ = ["Transformer", "PositionalEncoding", "predict", "rollout", "rollout_from_host", "HostRollout",
+__all__ = ["Transformer", "TransformerFuture", "Identity", "PositionalEncoding", "predict", "predict_diff",
+           "predict_future", "rollout", "rollout_from_host", "HostRollout",
            "rollout_sharded", "shard_bounds", "pe_index_for", "CONFIGS", "latent_dim", "parse_config_args",
            "LATENT_SCALE", "SOS_VALUE", "gemm", "build_library"]
 

@@ -455,15 +455,15 @@ class Engine {
   // Tile plan: trade wave quantisation (tiles vs. SMs / SM pairs) against per-tile efficiency.  The relative
   // efficiencies are measured on B200 (tools/gpu_check.py gemm_speed, profiles/), normalised to the 256x256 pair tile.
   TilePlan choose_plan(int M, int N, bool split) const {
-    // per-tile throughput relative to the 256x256 pair tile, measured at 8192^3 (MMA-bound regime) on B200:
-    //   one-CTA 128 x {64,128,256}: 524 / 859 / 1249 TFLOP/s;  pair 256 x {64,128,192,256}: 517 / 882 / 1130 / 1244.
-    // On the model's K=2048 shapes the pair kernel additionally wins on per-launch overhead, hence the 0.92.
+    // per-tile speed relative to the 256x256 pair tile, measured at 8192^3 on B200 (tools/gpu_check.py gemm_speed,
+    // profiles/README.md): one-CTA 128 x {64,128,256}: 605 / 932 / 1171 TFLOP/s; pair 256 x {64,128,192,256}:
+    // 678 / 991 / 1188 / 1337; split (3 MMAs per K step): pair 256x128 408-496, one-CTA 128x128 432.
     static const int bn1[4] = {32, 64, 128, 256};
-    static const double eff1[4] = {0.22, 0.42, 0.69, 0.92};
-    static const double eff1s[4] = {0.32, 0.55, 0.85, 0.0};
+    static const double eff1[4] = {0.25, 0.45, 0.70, 0.88};
+    static const double eff1s[4] = {0.10, 0.20, 0.32, 0.0};
     static const int bn2[4] = {64, 128, 192, 256};
-    static const double eff2[4] = {0.42, 0.71, 0.91, 1.0};
-    static const double eff2s[4] = {0.60, 1.0, 0.0, 0.0};
+    static const double eff2[4] = {0.51, 0.74, 0.89, 1.0};
+    static const double eff2s[4] = {0.19, 0.305, 0.0, 0.0};
     TilePlan best{false, 32};
     double best_cost = 1e300;
     for (int i = 0; i < 4; ++i) {  // one-CTA 128 x bn: one tile per SM per round
@@ -763,9 +763,12 @@ class Engine {
     return SDVG_OK;
   }
 
-  int rollout(const float* ctx, int B, int C, int n_pred, int window, int faithful, const float* teacher,
+  int rollout(const float* ctx, int B, int C, int n_pred, int window, int flags, const float* teacher,
               const int* pe_index, float scale_in, float scale_out, float* out, cudaStream_t st) {
+    const int faithful = flags & 1;     // literal prediction/predict.py sequence
+    const bool residual = (flags & 2) != 0;  // prediction/predict_diff.py:33: prediction += second-to-last window frame
     if (!ctx || !out) return fail(SDVG_ERR_INVALID, "null tensor");
+    if (residual && C < 2 && !faithful) return fail(SDVG_ERR_INVALID, "residual prediction needs a window of at least 2 frames");
     if (B <= 0 || C <= 0 || n_pred <= 0 || window <= 0) return fail(SDVG_ERR_INVALID, "empty rollout");
     if (faithful && C != 5) return fail(SDVG_ERR_INVALID, "faithful mode replays prediction/predict.py, which uses exactly 5 context frames");
     const int Hn = C + n_pred;
@@ -821,6 +824,17 @@ class Engine {
       oe.out32 = hist + static_cast<size_t>(C + t) * E; oe.ld32 = static_cast<int>(hstride); oe.row_map = 2;
       e = run_model(B, S, S, true, 1, nullptr, pe, oe, st, cached ? &cstep : nullptr);
       if (e != cudaSuccess) return fail_cuda(e, "rollout step");
+      if (residual) {
+        if (S < 2) return fail(SDVG_ERR_INVALID, "residual prediction needs a window of at least 2 frames");
+        AddArgs ad{};
+        ad.dst = hist + static_cast<size_t>(C + t) * E; ad.dst_clip_stride = hstride;
+        const int s2 = seq[S - 2];
+        ad.src = s2 >= 0 ? hist + static_cast<size_t>(s2) * E : nullptr; ad.src_clip_stride = hstride;
+        ad.fill = 2.0f;  // the SOS frame, if it is the second-to-last token
+        ad.clips = B; ad.width = E;
+        Scope sc(this, KC_PACK, 0.0, 12.0 * B * E, st);
+        if ((e = launch_add_rows(ad, num_sms, st)) != cudaSuccess) return fail_cuda(e, "residual add");
+      }
       if (teacher) {
         // export this prediction, then overwrite the slot with the teacher frame
         PackArgs x{};

@@ -53,6 +53,41 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackA
   }
 }
 
+// dst[b][:] += src[b][:]  (or += fill when src == nullptr): the residual prediction of the reference's
+// prediction/predict_diff.py:33  (pred[:, -1] = pred[:, -1] + y_input[:, -2]).
+struct AddArgs {
+  float* dst; long long dst_clip_stride;
+  const float* src; long long src_clip_stride;
+  float fill;
+  int clips, width;
+};
+
+__global__ void __launch_bounds__(256) add_rows_kernel(const __grid_constant__ AddArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const int w4 = a.width >> 2;
+  const long long total = static_cast<long long>(a.clips) * w4;
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
+    const int c4 = static_cast<int>(idx % w4);
+    const long long b = idx / w4;
+    float4* d = reinterpret_cast<float4*>(a.dst + b * a.dst_clip_stride) + c4;
+    float4 v = *d;
+    const float4 s = a.src ? __ldg(reinterpret_cast<const float4*>(a.src + b * a.src_clip_stride) + c4)
+                           : make_float4(a.fill, a.fill, a.fill, a.fill);
+    v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+    *d = v;
+  }
+}
+
+inline cudaError_t launch_add_rows(const AddArgs& a, int num_sms, cudaStream_t stream) {
+  const long long total = static_cast<long long>(a.clips) * (a.width >> 2);
+  if (total == 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  return launch_kernel(add_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a);
+}
+
 inline cudaError_t launch_pack(const PackArgs& a, int num_sms, cudaStream_t stream) {
   if (a.width % 4 != 0 || a.tokens > kPackMaxTokens) return cudaErrorInvalidValue;
   const long long total = static_cast<long long>(a.clips) * a.tokens * (a.width >> 2);

@@ -87,11 +87,11 @@ int sdvg_forward(sdvg_handle* h, const float* src, const float* tgt, int32_t B, 
 }
 
 int sdvg_rollout(sdvg_handle* h, const float* ctx, int32_t B, int32_t C, int32_t n_pred, int32_t window,
-                 int32_t faithful, const float* teacher, const int32_t* pe_index, float scale_in, float scale_out,
+                 int32_t flags, const float* teacher, const int32_t* pe_index, float scale_in, float scale_out,
                  float* out, void* stream) {
   if (!h) return SDVG_ERR_INVALID;
   cudaSetDevice(h->eng.cfg.device);
-  return h->eng.rollout(ctx, B, C, n_pred, window, faithful, teacher, pe_index, scale_in, scale_out, out,
+  return h->eng.rollout(ctx, B, C, n_pred, window, flags, teacher, pe_index, scale_in, scale_out, out,
                         static_cast<cudaStream_t>(stream));
 }
 

@@ -21,14 +21,34 @@ def predict(model, input_sequence):
     return pred[0, -1]
 
 
-def rollout(model, ctx, n_pred, window=5, *, use_sos=False, teacher=None, pe_index=None, scale_in=1.0,
-            scale_out=1.0, out=None):
-    """ctx (B,C,E) device tensor -> (B,n_pred,E).  ``use_sos=True`` replays the literal predict.py sequence
-    ([SOS,f1..f5] first, then the last 5 of [f1..f4,p1..pk]); otherwise a plain sliding window."""
+def predict_diff(model, input_sequence):
+    """prediction/predict_diff.py:14-41: residual prediction - the model output for the last position plus the
+    second-to-last input frame (:33).  Returns pred[0,-1] like the reference."""
     model.eval()
     with torch.no_grad():
-        return model.rollout(ctx, n_pred, window, faithful=use_sos, teacher=teacher, pe_index=pe_index,
-                             scale_in=scale_in, scale_out=scale_out, out=out)
+        pred = model(input_sequence, input_sequence, "causal").permute(1, 0, 2)
+        last = pred[:, -1, :] + input_sequence[:, -2, :]
+    return last[0]
+
+
+def predict_future(model, input_sequence):
+    """prediction/predict_future.py:16-42 (and the one-shot call at :156): no target mask, every position of the
+    output is a predicted frame.  Returns pred[0,-1] like the reference; ``model(x, x, None)`` gives all frames."""
+    model.eval()
+    with torch.no_grad():
+        pred = model(input_sequence, input_sequence, None).permute(1, 0, 2)
+    return pred[0, -1]
+
+
+def rollout(model, ctx, n_pred, window=5, *, use_sos=False, residual=False, teacher=None, pe_index=None,
+            scale_in=1.0, scale_out=1.0, out=None):
+    """ctx (B,C,E) device tensor -> (B,n_pred,E).  ``use_sos=True`` replays the literal predict.py sequence
+    ([SOS,f1..f5] first, then the last 5 of [f1..f4,p1..pk]); otherwise a plain sliding window.
+    ``residual=True`` is the predict_diff.py loop (each prediction += second-to-last window frame)."""
+    model.eval()
+    with torch.no_grad():
+        return model.rollout(ctx, n_pred, window, faithful=use_sos, residual=residual, teacher=teacher,
+                             pe_index=pe_index, scale_in=scale_in, scale_out=scale_out, out=out)
 
 
 class HostRollout:

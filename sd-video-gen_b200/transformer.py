@@ -107,6 +107,8 @@ class Transformer(nn.Module):
         stamp = self._stamp()
         if stamp != self._weights_stamp:
             for k, v in self.state_dict().items():
+                if k == "learned_tgt":      # TransformerFuture's extra parameter is not used by forward
+                    continue
                 t = v.detach()
                 if t.dtype != torch.float32 or not t.is_contiguous():
                     t = t.float().contiguous()
@@ -190,8 +192,8 @@ class Transformer(nn.Module):
         return matrix == pad_token
 
     # ------------------------------------------------------------------ rollout (prediction/predict.py)
-    def rollout(self, ctx, n_pred, window=5, *, faithful=False, teacher=None, pe_index=None, scale_in=1.0,
-                scale_out=1.0, out=None):
+    def rollout(self, ctx, n_pred, window=5, *, faithful=False, residual=False, teacher=None, pe_index=None,
+                scale_in=1.0, scale_out=1.0, out=None):
         """Batched autoregressive rollout on the device: ctx (B,C,E) -> (B,n_pred,E).  See sdvg_rollout."""
         self._check_eval()
         if ctx.dim() != 3 or ctx.size(2) != self.latent_dim:
@@ -220,7 +222,8 @@ class Transformer(nn.Module):
                 tuple(out.shape) != (B, n_pred, self.latent_dim):
             raise RuntimeError("out must be a contiguous fp32 (B, n_pred, E) tensor on the model's device")
         stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(_lib.load().sdvg_rollout(h, c.data_ptr(), B, Cn, n_pred, window, 1 if faithful else 0, tptr, pe_ptr,
+        _lib.check(_lib.load().sdvg_rollout(h, c.data_ptr(), B, Cn, n_pred, window,
+                                            (1 if faithful else 0) | (2 if residual else 0), tptr, pe_ptr,
                                             float(scale_in), float(scale_out), out.data_ptr(), C.c_void_p(stream)), h)
         return out
 
@@ -244,3 +247,41 @@ class Transformer(nn.Module):
         n = C.c_size_t()
         _lib.check(_lib.load().sdvg_workspace_bytes(self._handle, C.byref(n)), self._handle)
         return n.value
+
+
+class TransformerFuture(Transformer):
+    """Drop-in for models/transformer_future.py:9-94: the same network plus the (unused in forward) parameter
+    ``learned_tgt`` of shape (1, FRAMES_TO_PREDICT, E) (transformer_future.py:46-47), so its checkpoints load.
+    Used one-shot with ``tgt_mask=None`` (prediction/predict_future.py:24,156)."""
+
+    def __init__(self, num_tokens=0, dim_model=256, num_heads=8, num_encoder_layers=6, num_decoder_layers=6,
+                 dropout_p=0.1, *, frames_to_predict=None, **kw):
+        super().__init__(num_tokens, dim_model, num_heads, num_encoder_layers, num_decoder_layers, dropout_p, **kw)
+        if frames_to_predict is None:
+            frames_to_predict = self.config.FRAMES_TO_PREDICT[0]
+        self.learned_tgt = nn.Parameter(torch.randn((1, frames_to_predict, self.latent_dim), dtype=torch.float32),
+                                        requires_grad=True)
+
+    def _stamp(self):
+        return tuple(x for x in super()._stamp() if x[0] != "learned_tgt")
+
+    def state_dict_for_engine(self):
+        return {k: v for k, v in self.state_dict().items() if k != "learned_tgt"}
+
+
+class Identity(nn.Module):
+    """Drop-in for models/identity.py:9-41, the copy-last-frame baseline: forward returns ``src[:, -1:]``."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, src, tgt, tgt_mask=None, src_pad_mask=None, tgt_pad_mask=None):
+        return src[:, -1:]
+
+    def get_tgt_mask(self, size) -> torch.Tensor:
+        mask = torch.tril(torch.ones(size, size) == 1).float()
+        mask = mask.masked_fill(mask == 0, float("-inf"))
+        return mask.masked_fill(mask == 1, float(0.0))
+
+    def create_pad_mask(self, matrix: torch.Tensor, pad_token: int) -> torch.Tensor:
+        return matrix == pad_token

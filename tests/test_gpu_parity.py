@@ -194,3 +194,32 @@ def test_token_local_cache_is_exact(monkeypatch):
         if flag == "1":
             ref = outs["0", prec, kind]
             assert R.max_rel_per_frame(v.cpu(), ref.cpu()).max() < 1e-6, (prec, kind)
+
+
+def test_sibling_variants():
+    """predict_diff residual prediction (prediction/predict_diff.py:33), the one-shot unmasked
+    call of predict_future.py:156, TransformerFuture checkpoints, the Identity baseline."""
+    g = load_golden("small_rollout")
+    m, ref = ours_from(g, "fp32")
+    ctx = g["ctx"].to(DEV)
+    with torch.no_grad():
+        want = R.rollout_ref(ref, g["ctx"], 3, 5, residual=True)
+        got = sdvg_b200.rollout(m, ctx, 3, 5, residual=True).cpu()
+        assert R.max_rel_per_frame(got, want).max() < TOL32
+        wf = R.rollout_faithful(ref, g["frames"], 3, residual=True)
+        gf = sdvg_b200.rollout(m, g["frames"].to(DEV), 3, 5, use_sos=True, residual=True).cpu()
+        assert R.max_rel_per_frame(gf, wf).max() < TOL32
+        x = g["ctx"][:, -5:]
+        assert maxrel(sdvg_b200.predict_diff(m, x.to(DEV)), R.predict_diff_ref(ref, x)[0]) < TOL32
+        fut = ref(x, x, None).permute(1, 0, 2)                                       # predict_future.py:156
+        assert maxrel(m(x.to(DEV), x.to(DEV), None).permute(1, 0, 2), fut) < TOL32
+        assert maxrel(sdvg_b200.predict_future(m, x.to(DEV)), fut[0, -1]) < TOL32
+    d, H, Le, Ld, E = (int(v) for v in g["arch"])
+    mf = sdvg_b200.TransformerFuture(0, d, H, Le, Ld, 0.1, frame_size=64, frames_to_predict=5, precision="fp32")
+    sd = dict(ref.state_dict()); sd["learned_tgt"] = torch.zeros(1, 5, E)            # transformer_future.py:46-47
+    mf.load_state_dict(sd)
+    mf = mf.eval().to(DEV)
+    with torch.no_grad():
+        assert maxrel(mf(x.to(DEV), x.to(DEV), None).permute(1, 0, 2), fut) < TOL32
+    ident = sdvg_b200.Identity()
+    assert torch.equal(ident(ctx, ctx), ctx[:, -1:])

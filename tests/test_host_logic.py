@@ -126,3 +126,14 @@ def test_sharded_rollout_equals_chunked_reference_gloo(tmp_path):
     got, want = torch.load(tmp)
     assert got.shape == want.shape == (130, 2, 256)
     assert R.max_rel_per_frame(got, want).max() < 5e-5
+
+
+def test_sibling_modules_on_cpu():
+    m = sdvg_b200.TransformerFuture(0, 32, 4, 1, 1, 0.1, frame_size=64, frames_to_predict=5)
+    keys = set(m.state_dict())
+    base = set(sdvg_b200.Transformer(0, 32, 4, 1, 1, 0.1, frame_size=64).state_dict())
+    assert keys == base | {"learned_tgt"} and tuple(m.learned_tgt.shape) == (1, 5, 256)
+    ident = sdvg_b200.Identity()
+    x = torch.arange(24.0).view(2, 3, 4)
+    assert torch.equal(ident(x, x), x[:, -1:])                       # models/identity.py:13-16
+    assert torch.equal(ident.get_tgt_mask(4), m.get_tgt_mask(4))
