@@ -241,12 +241,18 @@ def run_ours(a, cfg, E):
     prof = model.timing_read()
     model.timing(False)
     pk = peaks()
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    if os.path.exists(tpath) and a.config == "1_15_kitti_L1_64" and B == 1024 and a.precision in ("mixed", "fp16"):
+        tj = json.load(open(tpath))      # dram__bytes_read+write per launch of the dominant GEMM instantiation (ncu --set full)
+        traffic, traffic_note = tj["traffic_bytes_per_launch"], f'{tj["kernel"]}; algorithmic {tj["algorithmic_bytes_per_launch"]} B; {tj["source"]}'
     cls = "gemm_tc" if prof["gemm_tc"]["launches"] else "gemm_simt"
     gk = prof[cls]
     achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12 if gk["ms"] > 0 else 0.0
     total_ms = sum(v["ms"] for v in prof.values())
     roofline = {"bound": "tensor", "kernel": f"sdvg::gemm_tc_kernel ({cls})", "achieved": achieved, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": pk["source"],
                 "launches_per_step": gk["launches"], "avg_launch_us": gk["ms"] * 1e3 / max(1, gk["launches"]),
                 "share_of_step": gk["ms"] / total_ms if total_ms else None,
                 "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
