@@ -141,6 +141,7 @@ class Engine {
   }
 
   ~Engine() {
+    destroy_graphs();
     for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
     for (void* p : allocs) cudaFree(p);
@@ -360,6 +361,7 @@ class Engine {
       const size_t slots_total = static_cast<size_t>(c.max_clips) * c.max_history;
       if ((e = dalloc(&hist, slots_total * E)) != cudaSuccess) return fail_cuda(e, "history alloc");
       if (const char* v = std::getenv("SDVG_CACHE")) use_cache = std::atoi(v) != 0;
+      if (const char* v = std::getenv("SDVG_GRAPH")) use_graphs = std::atoi(v) != 0;
       if (use_cache && ((e = dalloc(&c_emb, slots_total * d)) != cudaSuccess ||
                         (e = dalloc(&c_qkv_e, slots_total * 3 * d)) != cudaSuccess ||
                         (e = dalloc(&c_qkv_d, slots_total * 3 * d)) != cudaSuccess))
@@ -778,6 +780,98 @@ class Engine {
                   B, Hn, max_S, cfg.max_clips, cfg.max_history, cfg.max_tokens);
     int r = check_ready(st);
     if (r != SDVG_OK) return r;
+    RolloutKey key{ctx, teacher, pe_index, out, B, C, n_pred, window, flags, scale_in, scale_out};
+    return rollout_graphed(key, st);
+  }
+
+  // ------------------------------------------------------------------ CUDA-graph replay of a rollout
+  // One rollout is ~130 launches per predicted frame; at small batch the kernels are 5-15 us each and the host
+  // launch path becomes visible.  The second call with identical arguments captures the whole launch sequence
+  // (PDL edges included) into a CUDA graph on an internal stream and later calls replay it.
+  struct RolloutKey {
+    const float* ctx; const float* teacher; const int* pe_index; float* out;
+    int B, C, n_pred, window, flags; float scale_in, scale_out;
+    bool operator==(const RolloutKey& o) const {
+      return ctx == o.ctx && teacher == o.teacher && pe_index == o.pe_index && out == o.out && B == o.B && C == o.C &&
+             n_pred == o.n_pred && window == o.window && flags == o.flags && scale_in == o.scale_in && scale_out == o.scale_out;
+    }
+  };
+  struct GraphEntry { RolloutKey key; cudaGraphExec_t exec; int64_t launches; int uses; };
+  std::vector<GraphEntry> graphs;
+  std::vector<RolloutKey> seen_keys;
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;
+  bool use_graphs = true;
+
+  void destroy_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+    if (graph_stream) { cudaStreamDestroy(graph_stream); graph_stream = nullptr; }
+    if (graph_ev_in) { cudaEventDestroy(graph_ev_in); graph_ev_in = nullptr; }
+    if (graph_ev_out) { cudaEventDestroy(graph_ev_out); graph_ev_out = nullptr; }
+  }
+
+  int rollout_graphed(const RolloutKey& k, cudaStream_t st) {
+    if (!use_graphs || timing) return rollout_enqueue(k, st);
+    for (auto& g : graphs) {
+      if (g.key == k) return replay(g, st);
+    }
+    bool seen = false;
+    for (auto& sk : seen_keys) seen = seen || (sk == k);
+    if (!seen) {  // first call: run eagerly (also sets every kernel's launch attributes outside of capture)
+      if (seen_keys.size() >= 8) seen_keys.erase(seen_keys.begin());
+      seen_keys.push_back(k);
+      return rollout_enqueue(k, st);
+    }
+    if (!graph_stream) {
+      if (cudaStreamCreateWithFlags(&graph_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&graph_ev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&graph_ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError(); use_graphs = false;
+        return rollout_enqueue(k, st);
+      }
+    }
+    const int64_t before = launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(graph_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc = SDVG_OK;
+    if (ok) {
+      rc = rollout_enqueue(k, graph_stream);
+      ok = cudaStreamEndCapture(graph_stream, &graph) == cudaSuccess && rc == SDVG_OK && graph != nullptr;
+    }
+    const int64_t captured = launches - before;
+    launches = before;  // captured launches have not run
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {  // capture is an optimisation only: fall back to the eager CUDA path, permanently for this handle
+      cudaGetLastError(); use_graphs = false;
+      return rollout_enqueue(k, st);
+    }
+    if (graphs.size() >= 4) { cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
+    graphs.push_back(GraphEntry{k, exec, captured, 0});
+    return replay(graphs.back(), st);
+  }
+
+  int replay(GraphEntry& g, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(graph_ev_in, st);                        // order after the caller's stream
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(graph_stream, graph_ev_in, 0);
+    if (e == cudaSuccess) e = cudaGraphLaunch(g.exec, graph_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(graph_ev_out, graph_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, graph_ev_out, 0);      // and the caller's stream after the graph
+    if (e != cudaSuccess) return fail_cuda(e, "graph replay");
+    launches += g.launches;
+    ++g.uses;
+    return SDVG_OK;
+  }
+
+  int rollout_enqueue(const RolloutKey& k, cudaStream_t st) {
+    const float* ctx = k.ctx; const float* teacher = k.teacher; const int* pe_index = k.pe_index; float* out = k.out;
+    const int B = k.B, C = k.C, n_pred = k.n_pred, window = k.window;
+    const int faithful = k.flags & 1;
+    const bool residual = (k.flags & 2) != 0;
+    const float scale_in = k.scale_in, scale_out = k.scale_out;
+    const int Hn = C + n_pred;
     const int E = cfg.latent_dim;
     const long long hstride = static_cast<long long>(Hn) * E;
     const int* pe = pe_index ? pe_index : pe_mod64;

@@ -223,3 +223,27 @@ def test_sibling_variants():
         assert maxrel(mf(x.to(DEV), x.to(DEV), None).permute(1, 0, 2), fut) < TOL32
     ident = sdvg_b200.Identity()
     assert torch.equal(ident(ctx, ctx), ctx[:, -1:])
+
+
+def test_cuda_graph_replay_matches_eager(monkeypatch):
+    """The third call with identical arguments replays a captured CUDA graph (second call captures): same bits,
+    same launch accounting; new input values in the same buffer are honoured; SDVG_GRAPH=0 stays eager."""
+    g = load_golden("small_rollout")
+    m, _ = ours_from(g, "fp32")
+    ctx = g["ctx"].to(DEV).clone()
+    out = torch.empty(4, 4, 256, device=DEV)
+    n0 = m.launch_count()
+    a = sdvg_b200.rollout(m, ctx, 4, 5, out=out).clone(); n1 = m.launch_count()
+    b = sdvg_b200.rollout(m, ctx, 4, 5, out=out).clone(); n2 = m.launch_count()     # capture + first replay
+    c = sdvg_b200.rollout(m, ctx, 4, 5, out=out).clone(); n3 = m.launch_count()     # replay
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert n2 - n1 == n3 - n2 > 0 and n1 - n0 >= n2 - n1      # the first call also packs the weight planes
+    assert R.max_rel_per_frame(c.cpu(), g["free5"]).max() < TOL32
+    ctx.mul_(0.5)                                                                      # same pointer, new contents
+    d = sdvg_b200.rollout(m, ctx, 4, 5, out=out).clone()
+    monkeypatch.setenv("SDVG_GRAPH", "0")
+    m2, _ = ours_from(g, "fp32")
+    e1 = sdvg_b200.rollout(m2, ctx, 4, 5)
+    e2 = sdvg_b200.rollout(m2, ctx, 4, 5)
+    e3 = sdvg_b200.rollout(m2, ctx, 4, 5)
+    assert torch.equal(d, e3) and torch.equal(e1, e3) and torch.equal(e2, e3)
