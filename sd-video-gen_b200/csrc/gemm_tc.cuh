@@ -103,16 +103,68 @@ __device__ __forceinline__ uint2 pack_lo4(const float4& v, const uint2& hi) {
 // per-element address arithmetic, integer division and generic-space smem accesses (~18 us per 128x256 tile,
 // longer than the tile's MMA main loop), so everything row- or tile-invariant is hoisted and the staging
 // buffer is addressed in the shared window explicitly.
-template <int BN, bool SPLIT, bool FANCY, typename Release>
+// Bias / residual operands of up to PF 32-column chunks, loaded ahead of use.  The epilogue warps fill this for
+// the NEXT tile before they block on its accumulator barrier, so the ~1 us L2 latency of the residual rows is
+// hidden behind the tile's MMA main loop (with a one-chunk look-ahead the last tile's epilogue - which nothing
+// overlaps - still took 4 us of a 32 us launch; see tools/gemm_trace.py).
+template <int PF>
+struct EpiPre {
+  float4 b4[PF];
+  float4 res[PF][8];
+};
+
+template <bool FANCY>
+__device__ __forceinline__ void epi_prefetch_chunk(const TcGemmArgs& args, int row0, int col, int lr, float4& b4,
+                                                   float4 (&res)[8]) {
+  const Epilogue& e = args.epi;
+  const int rows_valid = args.M - row0;
+  b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < args.N) {
+    if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    if (e.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + lr;
+        size_t rrow = static_cast<size_t>(row0 + rr);
+        if constexpr (FANCY) rrow = static_cast<size_t>(epi_res_row(e, row0 + rr));
+        res[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(e.residual + rrow * e.ld_res + col))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+// Issue the loads of the first min(NCW, PF) chunks of a tile (chunks c0 .. c0+NCW-1 belong to this warp).
+template <bool FANCY, int NCW, int PF>
+__device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmArgs& args, int row0, int col_base, int lane, int c0,
+                                                     EpiPre<PF>& pre) {
+  if (!args.vec4) return;
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll
+  for (int j = 0; j < (NCW < PF ? NCW : PF); ++j)
+    epi_prefetch_chunk<FANCY>(args, row0, col_base + (c0 + j) * 32 + lc, lr, pre.b4[j], pre.res[j]);
+}
+
+// Epilogue of one accumulator tile for one warp: 32 TMEM lanes (rows row0..row0+31) x NCW chunks of 32 columns
+// starting at chunk c0 of the tile whose first global column is col_base.  TMEM -> registers -> padded smem
+// transpose -> row-contiguous 128-bit global accesses.  `release()` is called by lane 0 once every TMEM read of
+// the tile has completed (hands the accumulator back to the MMA issuer before the last global stores).
+// FANCY = false is the lean path of the 70-odd per-layer GEMMs (bias, ReLU, residual, fp32 / plane outputs);
+// FANCY = true adds what only a few GEMMs need (scale, positional rows, row remapping, clip-strided residual).
+// The first version of this routine was one generic loop; ncu showed the epilogue warps issue-bound on
+// per-element address arithmetic, integer division and generic-space smem accesses (~18 us per 128x256 tile,
+// longer than the tile's MMA main loop), so everything row- or tile-invariant is hoisted and the staging
+// buffer is addressed in the shared window explicitly.
+template <int BN, bool SPLIT, bool FANCY, int NCW, int PF, typename Release>
 __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* stg, uint32_t tbase, int row0,
-                                                 int col_base, int lane, int c_begin, int c_end, Release release) {
+                                                 int col_base, int lane, int c0, EpiPre<PF>& pre, Release release) {
   const Epilogue& e = args.epi;
   const int M = args.M, N = args.N;
   const uint32_t stg_addr = ptx::smem_u32(stg);
   if (!args.vec4) {
     // unaligned / odd-N fallback: one column per lane, one row per pass (never on the model's hot path)
 #pragma unroll 1
-    for (int c = c_begin; c < c_end; ++c) {
+    for (int c = c0; c < c0 + NCW; ++c) {
       uint32_t r0[32];
       ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
       if (SPLIT) {
@@ -126,7 +178,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(stg_addr + (lane * kTcEpiStride + 4 * j) * 4, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-      if (c == c_end - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) release(); } else { __syncwarp(); }
+      if (c == c0 + NCW - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) release(); } else { __syncwarp(); }
       const int col = col_base + c * 32 + lane;
       if (col < N) {
         for (int r = 0; r < 32; ++r) {
@@ -144,41 +196,20 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
   // transposed read-back: 8 lanes x float4 cover the 32 columns of one row, 4 rows per pass, 8 passes
   const int lr = lane >> 3, lc = (lane & 7) * 4;
   const int rows_valid = M - row0;  // rows of this warp's slab inside the matrix (>= 32: all)
-  const float* bias = e.bias;
   const float* residual = e.residual;
   float* out32 = e.out32;
   uint16_t* out_hi = e.out_hi;
   uint16_t* out_lo = e.out_lo;
   const int relu = e.relu, bf16 = e.bf16;
-  const size_t ld_res = e.ld_res, ld32 = e.ld32, ld16 = e.ld16;
+  const size_t ld32 = e.ld32, ld16 = e.ld16;
   const uint32_t rd_addr = stg_addr + (lr * kTcEpiStride + lc) * 4;
   const uint32_t wr_addr = stg_addr + lane * kTcEpiStride * 4;
 
-  // software pipeline over the 32-column chunks: the bias and residual loads of chunk c+1 are in flight while
-  // chunk c is transposed and stored (the residual comes from L2 at ~1 us latency; serialising it per chunk made
-  // the epilogue ~8 us per 128x256 tile, all of it exposed on the last tile of every launch)
-  float4 b4_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 res_n[8];
-  auto prefetch = [&](int c) {
-    const int col = col_base + c * 32 + lc;
-    if (col < N) {
-      if (bias) b4_n = __ldg(reinterpret_cast<const float4*>(bias + col));
-      if (residual) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + lr;
-          size_t rrow = static_cast<size_t>(row0 + rr);
-          if constexpr (FANCY) rrow = static_cast<size_t>(epi_res_row(e, row0 + rr));
-          res_n[i] = rr < rows_valid ? __ldg(reinterpret_cast<const float4*>(residual + rrow * ld_res + col))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
-  };
-  if (c_begin < c_end) prefetch(c_begin);
-
-#pragma unroll 1
-  for (int c = c_begin; c < c_end; ++c) {
+  for (int j = 0; j < NCW; ++j) {
+    const int c = c0 + j;
+    constexpr int kNoSlot = 0;
+    (void)kNoSlot;
     uint32_t r0[32];
     ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
     if (SPLIT) {
@@ -191,19 +222,15 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
       ptx::tmem_ld_wait();
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(wr_addr + 16 * j, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-    if (c == c_end - 1) {
+    for (int u = 0; u < 8; ++u) sts128(wr_addr + 16 * u, r0[4 * u], r0[4 * u + 1], r0[4 * u + 2], r0[4 * u + 3]);
+    if (j == NCW - 1) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) release();
     } else {
       __syncwarp();
     }
-    const float4 b4 = b4_n;
-    float4 res[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) res[i] = res_n[i];
-    if (c + 1 < c_end) prefetch(c + 1);
+    const float4 b4 = pre.b4[j % PF];
     const int col = col_base + c * 32 + lc;
     if (col < N) {
 #pragma unroll
@@ -229,7 +256,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
             }
           }
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+          if (residual) {
+            const float4 rv = pre.res[j % PF][i];
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          }
           if (out32 && out_row >= 0) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(out_row) * ld32 + col) = v;
           if (out_hi) {
             const uint2 h = pack_hi4(v, bf16);
@@ -240,6 +270,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
         }
       }
     }
+    // this slot is free again: start the loads of chunk j + PF of this tile
+    if (j + PF < NCW)
+      epi_prefetch_chunk<FANCY>(args, row0, col_base + (c + PF) * 32 + lc, lr, pre.b4[j % PF], pre.res[j % PF]);
     __syncwarp();
   }
 }
@@ -369,19 +402,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int q = warp & 3;               // TMEM lane quadrant this warp is allowed to read
     const int half = (warp - 2) >> 2;     // which half of the tile's column chunks
     constexpr int kChunks = BN / 32;
-    const int c_begin = Cfg::kEpiActive == 8 ? half * (kChunks / 2) : 0;
-    const int c_end = Cfg::kEpiActive == 8 ? (half + 1) * (kChunks / 2) : (half == 0 ? kChunks : 0);
+    constexpr int NCW = Cfg::kEpiActive == 8 ? kChunks / 2 : kChunks;   // chunks per participating warp
+    constexpr int PF = NCW < 3 ? NCW : 3;
+    const bool active = Cfg::kEpiActive == 8 || half == 0;
+    const int c0 = Cfg::kEpiActive == 8 ? half * NCW : 0;
     float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles && c_begin < c_end; t += gridDim.x) {
+    for (int t = blockIdx.x; t < total_tiles && active; t += gridDim.x) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
+      const int row0 = m_blk * kTcBM + q * 32;
+      EpiPre<PF> pre;
+      tc_epilogue_prefetch<FANCY, NCW, PF>(args, row0, n_blk * BN, lane, c0, pre);
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
       uint64_t* done_bar = &tempty_bar[buf];
-      tc_epilogue_tile<BN, SPLIT, FANCY>(args, stg, tbase, m_blk * kTcBM + q * 32, n_blk * BN, lane, c_begin, c_end,
-                                         [done_bar]() { ptx::mbar_arrive(done_bar); });
+      tc_epilogue_tile<BN, SPLIT, FANCY, NCW, PF>(args, stg, tbase, row0, n_blk * BN, lane, c0, pre,
+                                                  [done_bar]() { ptx::mbar_arrive(done_bar); });
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   }

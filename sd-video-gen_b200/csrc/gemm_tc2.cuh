@@ -183,22 +183,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // ------------------------------------------------------------------ epilogue warps (own 128 rows, 2 per quadrant)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int kChunks = BN / 32;
-    const int c_begin = half * (kChunks / 2), c_end = (half + 1) * (kChunks / 2);
+    constexpr int NCW = BN / 64;              // 32-column chunks per warp
+    constexpr int PF = NCW < 3 ? NCW : 3;     // chunks whose bias / residual operands are loaded ahead
+    const int c0 = half * NCW;
     float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
     int buf = 0;
     uint32_t buf_phase = 0;
     int tile_no = 0;
     for (int t = pair; t < total_tiles; t += num_pairs, ++tile_no) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
+      const int row0 = m_blk * kTc2BM + static_cast<int>(rank) * kTcBM + q * 32;
+      EpiPre<PF> pre;
+      tc_epilogue_prefetch<FANCY, NCW, PF>(args, row0, n_blk * BN, lane, c0, pre);   // in flight during the main loop
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
       if (warp == 2 && lane == 0 && tile_no < 8) SDVG_TRACE(24 + tile_no);
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
       const uint32_t lead_tempty = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[buf]), 0);
-      tc_epilogue_tile<BN, SPLIT, FANCY>(args, stg, tbase, m_blk * kTc2BM + static_cast<int>(rank) * kTcBM + q * 32,
-                                         n_blk * BN, lane, c_begin, c_end,
-                                         [lead_tempty]() { ptx::mbar_arrive_cluster(lead_tempty); });
+      tc_epilogue_tile<BN, SPLIT, FANCY, NCW, PF>(args, stg, tbase, row0, n_blk * BN, lane, c0, pre,
+                                                  [lead_tempty]() { ptx::mbar_arrive_cluster(lead_tempty); });
       if (warp == 2 && lane == 0 && tile_no < 8) SDVG_TRACE(32 + tile_no);
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
