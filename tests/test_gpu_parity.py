@@ -247,3 +247,46 @@ def test_cuda_graph_replay_matches_eager(monkeypatch):
     e2 = sdvg_b200.rollout(m2, ctx, 4, 5)
     e3 = sdvg_b200.rollout(m2, ctx, 4, 5)
     assert torch.equal(d, e3) and torch.equal(e1, e3) and torch.equal(e2, e3)
+
+
+@pytest.mark.parametrize("name", ["11_27_ucf_final", "11_19_wallpushups_all_losses_test"])
+def test_other_baseline_architectures_vs_oracle(name):
+    """BASELINE configs C3 (d2048 H8 4e/8d, E=1024) and C5's architecture (d1024 H16 12e/12d, E=1024, head dim 64):
+    no golden file - the oracle (reference arithmetic on CPU, same seeded weights) is run here on a small batch."""
+    from oracle.ref_module import RefTransformer
+    c = sdvg_b200.CONFIGS[name]
+    torch.manual_seed(0)
+    ref = RefTransformer(0, c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"], 0.1,
+                         frame_size=c["frame_size"]).eval()
+    m = sdvg_b200.Transformer(0, c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"], 0.1,
+                              frame_size=c["frame_size"], precision="fp32")
+    m.load_state_dict(ref.state_dict())
+    m = m.eval().to(DEV)
+    ctx = torch.randn(4, 6, 1024, generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        want = R.rollout_ref(ref, ctx, 2, 5)
+        fwd = ref(ctx[:, :6], ctx[:, :5], ref.get_tgt_mask(5))                  # trainer shapes: S_src=6, S_tgt=5
+    assert R.max_rel_per_frame(sdvg_b200.rollout(m, ctx.to(DEV), 2, 5).cpu(), want).max() < TOL32
+    assert maxrel(m(ctx[:, :6].to(DEV), ctx[:, :5].contiguous().to(DEV), "causal"), fwd) < TOL32
+    m.set_precision("mixed")
+    tf = sdvg_b200.rollout(m, ctx.to(DEV), 2, 5, teacher=want.to(DEV)).cpu()
+    assert R.max_rel_per_frame(tf, want).max() < TOL16
+
+
+def test_edge_shapes():
+    """Single clip, single token, window longer than the history, maximum batch of the reference (64), 32-token window."""
+    g = load_golden("small_rollout")
+    m, ref = ours_from(g, "fp32")
+    with torch.no_grad():
+        x1 = torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(2))
+        assert maxrel(m(x1.to(DEV), x1.to(DEV), "causal"), ref(x1, x1, ref.get_tgt_mask(1))) < TOL32
+        c1 = torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(3))           # C=1, window 5: growing window
+        assert R.max_rel_per_frame(sdvg_b200.rollout(m, c1.to(DEV), 3, 5).cpu(), R.rollout_ref(ref, c1, 3, 5)).max() < TOL32
+        x32 = torch.randn(2, 32, 256, generator=torch.Generator().manual_seed(4))          # S = 32 (kernel limit)
+        assert maxrel(m(x32.to(DEV), x32.to(DEV), "causal"), ref(x32, x32, ref.get_tgt_mask(32))) < TOL32
+        x64 = torch.randn(64, 3, 256, generator=torch.Generator().manual_seed(5))
+        assert maxrel(m(x64.to(DEV), x64.to(DEV), None), ref(x64, x64, None)) < TOL32
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 33, 256, device=DEV), torch.zeros(2, 33, 256, device=DEV))       # beyond max tokens
+    with pytest.raises(RuntimeError):
+        sdvg_b200.rollout(m, torch.zeros(0, 5, 256, device=DEV), 2, 5)                     # empty batch
