@@ -23,6 +23,7 @@ struct AttnArgs {
   int mask_kind; const float* mask;
   float scale;
   int q_first;        // first query row to compute (Sq-1 when only the last token is needed)
+  int out_compact;    // 1: output rows are packed per clip from q_first on, i.e. row = b*(Sq-q_first) + (i-q_first)
   float* out32; int ld32;
   uint16_t* out_hi; uint16_t* out_lo; int ld16; int bf16;
 };
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
         for (int t = 0; t < EPL; ++t) ol[t] = fmaf(p, vl[t], ol[t]);
       }
     }
-    const size_t row = static_cast<size_t>(b) * a.Sq + i;
+    const size_t row = a.out_compact ? static_cast<size_t>(b) * (a.Sq - a.q_first) + (i - a.q_first) : static_cast<size_t>(b) * a.Sq + i;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int e0 = (c * 32 + lane) * VEC;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(128) attention_reg_kernel(const __grid_constan
         for (int t = 0; t < EPL; ++t) ol[t] = fmaf(p, vr[j][t], ol[t]);
       }
     }
-    const size_t row = static_cast<size_t>(b) * a.Sq + i;
+    const size_t row = a.out_compact ? static_cast<size_t>(b) * (a.Sq - a.q_first) + (i - a.q_first) : static_cast<size_t>(b) * a.Sq + i;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = h * hd + (c * 32 + lane) * VEC;
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(128) attention_exact_kernel(const __grid_const
 #pragma unroll
       for (int t = 0; t < EPL; ++t) ol[t] = fmaf(p, vr[j][t], ol[t]);
     }
-    const size_t row = static_cast<size_t>(b) * SQ + i;
+    const size_t row = a.out_compact ? static_cast<size_t>(b) * (SQ - a.q_first) + (i - a.q_first) : static_cast<size_t>(b) * SQ + i;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = h * hd + (c * 32 + lane) * VEC;
@@ -342,6 +343,9 @@ inline cudaError_t launch_attention_exact(const AttnArgs& a, int grid, cudaStrea
   if (a.Sq == 6 && a.Sk == 6) return launch_attention_exact_m<VEC, NCH, 6, 6>(a, grid, stream);
   if (a.Sq == 10 && a.Sk == 10) return launch_attention_exact_m<VEC, NCH, 10, 10>(a, grid, stream);
   if (a.Sq == 5 && a.Sk == 6) return launch_attention_exact_m<VEC, NCH, 5, 6>(a, grid, stream);
+  if (a.Sq == 1 && a.Sk == 5) return launch_attention_exact_m<VEC, NCH, 1, 5>(a, grid, stream);
+  if (a.Sq == 1 && a.Sk == 6) return launch_attention_exact_m<VEC, NCH, 1, 6>(a, grid, stream);
+  if (a.Sq == 1 && a.Sk == 10) return launch_attention_exact_m<VEC, NCH, 1, 10>(a, grid, stream);
   return cudaErrorNotSupported;
 }
 
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(128) attention_exact16_kernel(const __grid_con
 #pragma unroll
       for (int t = 0; t < VEC; ++t) ol[t] = fmaf(pj, vr[j][t], ol[t]);
     }
-    const size_t row = static_cast<size_t>(b) * SQ + i;
+    const size_t row = a.out_compact ? static_cast<size_t>(b) * (SQ - a.q_first) + (i - a.q_first) : static_cast<size_t>(b) * SQ + i;
     const int col = h * hd + lane * VEC;
     if (a.out32) {
 #pragma unroll
@@ -473,7 +477,8 @@ __global__ void __launch_bounds__(128) attention_exact16_kernel(const __grid_con
 
 // shapes the 16-bit-input kernel is instantiated for (the engine asks before choosing the 16-bit Q/K/V layout)
 inline bool attention16_supported(int hd, int Sq, int Sk, int mask_kind) {
-  const bool shape = (Sq == 5 && Sk == 5) || (Sq == 6 && Sk == 6) || (Sq == 10 && Sk == 10) || (Sq == 5 && Sk == 6);
+  const bool shape = (Sq == 5 && Sk == 5) || (Sq == 6 && Sk == 6) || (Sq == 10 && Sk == 10) || (Sq == 5 && Sk == 6) ||
+                     (Sq == 1 && (Sk == 5 || Sk == 6 || Sk == 10));
   return shape && (hd == 256 || hd == 128 || hd == 64 || hd == 32) && (mask_kind == 0 || mask_kind == 1);
 }
 
@@ -487,6 +492,9 @@ inline cudaError_t launch_attention16_v(const AttnArgs& a, int grid, cudaStream_
   if (a.Sq == 5 && a.Sk == 5) return launch_attention16_m<VEC, 5, 5>(a, grid, stream);
   if (a.Sq == 6 && a.Sk == 6) return launch_attention16_m<VEC, 6, 6>(a, grid, stream);
   if (a.Sq == 10 && a.Sk == 10) return launch_attention16_m<VEC, 10, 10>(a, grid, stream);
+  if (a.Sq == 1 && a.Sk == 5) return launch_attention16_m<VEC, 1, 5>(a, grid, stream);
+  if (a.Sq == 1 && a.Sk == 6) return launch_attention16_m<VEC, 1, 6>(a, grid, stream);
+  if (a.Sq == 1 && a.Sk == 10) return launch_attention16_m<VEC, 1, 10>(a, grid, stream);
   return launch_attention16_m<VEC, 5, 6>(a, grid, stream);
 }
 // Q/K/V given as 16-bit planes (a.q/a.k/a.v point at uint16 data; ldq/ldkv/clip strides in elements).

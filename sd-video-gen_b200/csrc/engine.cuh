@@ -109,6 +109,7 @@ class Engine {
   float* c_qkv_e = nullptr;  // [max_clips * max_history][3d]
   float* c_qkv_d = nullptr;  // [max_clips * max_history][3d]
   bool use_cache = true;
+  bool use_prune = true;     // last-decoder-layer pruning in rollouts (SDVG_PRUNE=0 disables)
   int* pe_mod64 = nullptr;   // [max_clips] b mod 64
 
   struct TimedSpan { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -349,7 +350,7 @@ class Engine {
     SDVG_ACT(mem, d, S, T, sa);
     SDVG_ACT(qc, d, true, false, false);
     SDVG_ACT(kvc, 2 * d, true, false, false);
-    SDVG_ACT(fin, d, S, T, sa);
+    SDVG_ACT(fin, d, true, T, sa);
 #undef SDVG_ACT
     if (qkv16_mode()) {
       if ((e = dalloc(&qkv16, static_cast<size_t>(max_rows) * 3 * d)) != cudaSuccess ||
@@ -362,6 +363,7 @@ class Engine {
       if ((e = dalloc(&hist, slots_total * E)) != cudaSuccess) return fail_cuda(e, "history alloc");
       if (const char* v = std::getenv("SDVG_CACHE")) use_cache = std::atoi(v) != 0;
       if (const char* v = std::getenv("SDVG_GRAPH")) use_graphs = std::atoi(v) != 0;
+      if (const char* v = std::getenv("SDVG_PRUNE")) use_prune = std::atoi(v) != 0;
       if (use_cache && ((e = dalloc(&c_emb, slots_total * d)) != cudaSuccess ||
                         (e = dalloc(&c_qkv_e, slots_total * 3 * d)) != cudaSuccess ||
                         (e = dalloc(&c_qkv_d, slots_total * 3 * d)) != cudaSuccess))
@@ -562,7 +564,8 @@ class Engine {
 
   cudaError_t attention(const float* q, int ldq, const float* k, const float* v, int ldkv, int B, int Sq, int Sk,
                         int mask_kind, const float* mask, int q_first, const ActBuf& dst, cudaStream_t st,
-                        long long q_clip_stride = 0, long long kv_clip_stride = 0, bool in16 = false) {
+                        long long q_clip_stride = 0, long long kv_clip_stride = 0, bool in16 = false,
+                        bool out_compact = false) {
     AttnArgs a{};
     a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv;
     a.q_clip_stride = q_clip_stride; a.kv_clip_stride = kv_clip_stride;
@@ -570,6 +573,7 @@ class Engine {
     a.mask_kind = mask_kind; a.mask = mask;
     a.scale = 1.0f / sqrtf(static_cast<float>(a.hd));
     a.q_first = q_first;
+    a.out_compact = out_compact ? 1 : 0;
     a.out32 = tc() ? nullptr : dst.f32; a.ld32 = dst.ld32;
     a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
     const double d = cfg.dim_model;
@@ -603,6 +607,85 @@ class Engine {
 
   // One pass of the model on operand buffers lat_s (and lat_t unless `same`).  `oe` describes where the
   // output latents go (fp32 destination, row mapping).
+  // Last decoder layer for the last token of every clip (see run_model).  Input stream: xt (all Mt rows, layer
+  // >= 1 so it is the LayerNorm'd stream).  Compact per-clip rows live in the first B rows of xt / ybuf / attn / ffh.
+  cudaError_t pruned_last_layer(const DecLayer& L, int B, int Ss, int St, int mask_kind, const float* mask, Epilogue oe,
+                                cudaStream_t st) {
+    const int d = cfg.dim_model, hd = d / cfg.num_heads;
+    const int Ms = B * Ss, Mt = B * St;
+    // self-attention: K|V for every row, Q for the last row of each clip only
+    const bool s16 = qkv16 && attention16_supported(hd, St, St, mask_kind);
+    {
+      Epilogue ekv;  // rows [d, 3d) of the packed in-proj = K|V  -> columns [d, 3d) of the qkv buffer
+      Epilogue eq;   // rows [0, d) = Q, last token only: A rows are clip-strided -> gather through a pruned GEMM below
+      if (s16) { ekv.out_hi = qkv16 + d; ekv.ld16 = 3 * d; }
+      else { ekv.out32 = qkv.f32 + d; ekv.ld32 = 3 * d; }
+      SDVG_CK(gemm(xt, L.sa.kv, Mt, ekv, st));
+      // Q: the GEMM A operand must be contiguous rows, so project all rows' Q only if St is tiny; otherwise use
+      // the packed last rows produced by last_rows() below
+      SDVG_CK(last_rows(xt, B, St, st));                       // xt rows (b*St + St-1) -> fin rows b (fp32 + planes)
+      if (s16) { eq.out_hi = qc16; eq.ld16 = d; }
+      else { out_to(eq, qc, true); eq.out_hi = nullptr; eq.out_lo = nullptr; }
+      SDVG_CK(gemm(fin, L.sa.q, B, eq, st));
+    }
+    // attention of the last query row against all keys of the clip (the causal mask allows all of them)
+    if (s16)
+      SDVG_CK(attention(reinterpret_cast<const float*>(qc16), d, reinterpret_cast<const float*>(qkv16 + d),
+                        reinterpret_cast<const float*>(qkv16 + 2 * d), 3 * d, B, 1, St, 0, nullptr, 0, attn, st, 0, 0, true));
+    else
+      SDVG_CK(attention(qc.f32, d, qkv.f32 + d, qkv.f32 + 2 * d, 3 * d, B, 1, St, 0, nullptr, 0, attn, st));
+    (void)mask; (void)Ms;
+    Epilogue eo;
+    eo.residual = fin.f32; eo.ld_res = fin.ld32;               // packed last rows of the input stream
+    out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+    SDVG_CK(gemm(attn, L.sa.out, B, eo, st));
+    SDVG_CK(layernorm(ybuf, B, L.n1, nullptr, xt, true, 1, 0, st));          // xt rows [0, B): compact stream
+    // cross attention: one query per clip, K/V from the whole encoder memory
+    Epilogue eq2, ekv2;
+    if (qkv16 && attention16_supported(hd, 1, Ss, 0)) {
+      eq2.out_hi = qc16; eq2.ld16 = d;
+      SDVG_CK(gemm(xt, L.ca.q, B, eq2, st));
+      ekv2.out_hi = kvc16; ekv2.ld16 = 2 * d;
+      SDVG_CK(gemm(mem, L.ca.kv, B * Ss, ekv2, st));
+      SDVG_CK(attention(reinterpret_cast<const float*>(qc16), d, reinterpret_cast<const float*>(kvc16),
+                        reinterpret_cast<const float*>(kvc16 + d), 2 * d, B, 1, Ss, 0, nullptr, 0, attn, st, 0, 0, true));
+    } else {
+      out_to(eq2, qc, true); eq2.out_hi = nullptr; eq2.out_lo = nullptr;
+      SDVG_CK(gemm(xt, L.ca.q, B, eq2, st));
+      out_to(ekv2, kvc, true); ekv2.out_hi = nullptr; ekv2.out_lo = nullptr;
+      SDVG_CK(gemm(mem, L.ca.kv, B * Ss, ekv2, st));
+      SDVG_CK(attention(qc.f32, d, kvc.f32, kvc.f32 + d, 2 * d, B, 1, Ss, 0, nullptr, 0, attn, st));
+    }
+    Epilogue eo2;
+    eo2.residual = xt.f32; eo2.ld_res = xt.ld32;
+    out_to(eo2, ybuf, true); eo2.out_hi = nullptr; eo2.out_lo = nullptr;
+    SDVG_CK(gemm(attn, L.ca.out, B, eo2, st));
+    SDVG_CK(layernorm(ybuf, B, L.n2, nullptr, xt, true, 1, 0, st));
+    // feed-forward, norm3 chained with decoder.norm
+    Epilogue e1;
+    e1.relu = 1;
+    out_to(e1, ffh, !tc());
+    SDVG_CK(gemm(xt, L.ff1, B, e1, st));
+    Epilogue e2;
+    e2.residual = xt.f32; e2.ld_res = xt.ld32;
+    out_to(e2, ybuf, true); e2.out_hi = nullptr; e2.out_lo = nullptr;
+    SDVG_CK(gemm(ffh, L.ff2, B, e2, st));
+    SDVG_CK(layernorm(ybuf, B, L.n3, &dec_norm, fin, false, 1, 0, st));
+    // output projection of the B last-token rows straight into the destination (row b -> oe.out32 + b * ld32)
+    oe.row_map = 0; oe.rows_per_clip = 1; oe.clips = B;
+    return gemm(fin, out_proj, B, oe, st);
+  }
+
+  // Gather the last token row of every clip of a stream into the first B rows of `fin` (fp32 + operand planes).
+  cudaError_t last_rows(const ActBuf& x, int B, int S, cudaStream_t st) {
+    PackArgs a{};
+    a.src = x.f32 + static_cast<size_t>(S - 1) * x.ld32; a.src_clip_stride = static_cast<long long>(S) * x.ld32; a.src_slot_stride = 0;
+    a.clips = B; a.tokens = 1; a.width = cfg.dim_model; a.slot[0] = 0; a.scale = 1.0f;
+    a.out32 = fin.f32 ? fin.f32 : nullptr; a.out_clip_stride = fin.ld32; a.out_tok_stride = 0;
+    a.out_hi = fin.p.hi; a.out_lo = fin.p.lo; a.ld16 = fin.p.ld; a.bf16 = bf16();
+    return pack(a, st);
+  }
+
   // Token-local cache step of the rollout: lat_s holds only the `n_new` newest tokens of the window (the last
   // n_new positions); cache rows of clip b are slots [b*Hn, (b+1)*Hn), the window starts at slot `first`.
   struct CacheStep { int Hn, first, n_new; };
@@ -701,7 +784,15 @@ class Engine {
     // ---------------- decoder
     const ActBuf* y = &emb_s;
     if (!same) { SDVG_CK(embed(lat_t, St, emb_t)); y = &emb_t; }
+    // Exact pruning of the last decoder layer (rollout only keeps the last token, prediction/predict.py:42): its
+    // self-attention K/V need every row, but Q, both out-projections, the cross-attention query, the FFN, the
+    // final norms and the output projection are computed for the last token of each clip only (M = B rows).
+    const bool prune = (oe.row_map == 2) && Ld >= 2 && St >= 2 && use_prune;
     for (int l = 0; l < Ld; ++l) {
+      if (prune && l == Ld - 1) {
+        SDVG_CK(pruned_last_layer(dec[l], B, Ss, St, mask_kind, mask, oe, st));
+        return cudaSuccess;
+      }
       if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_d, dec[l].sa, St, Mt, mask_kind, dec[l].n1, xt));
       else SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt, l == 0));
       // cross attention: Q from the target stream, K/V from the encoder memory

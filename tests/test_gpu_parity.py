@@ -290,3 +290,22 @@ def test_edge_shapes():
         m(torch.zeros(2, 33, 256, device=DEV), torch.zeros(2, 33, 256, device=DEV))       # beyond max tokens
     with pytest.raises(RuntimeError):
         sdvg_b200.rollout(m, torch.zeros(0, 5, 256, device=DEV), 2, 5)                     # empty batch
+
+
+def test_last_layer_pruning_is_exact(monkeypatch):
+    """Rollouts compute the last decoder layer for the last token of each clip only (predict.py:42 keeps nothing
+    else).  Same results as the full layer, for fixed, growing and odd windows and for 16-bit modes."""
+    g = load_golden("small_rollout")
+    ctx = torch.randn(70, 7, 256, generator=torch.Generator().manual_seed(18)).to(DEV)
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SDVG_PRUNE", flag)
+        for prec in ("fp32", "mixed"):
+            m, _ = ours_from(g, prec)
+            outs[flag, prec, "w5"] = sdvg_b200.rollout(m, ctx, 4, 5)
+            outs[flag, prec, "w7"] = sdvg_b200.rollout(m, ctx, 3, 7)
+            outs[flag, prec, "grow"] = sdvg_b200.rollout(m, ctx[:, :2], 5, 6)
+            outs[flag, prec, "sos"] = sdvg_b200.rollout(m, ctx[:, :5], 3, 5, use_sos=True)
+    for (flag, prec, kind), v in outs.items():
+        if flag == "1":
+            assert R.max_rel_per_frame(v.cpu(), outs["0", prec, kind].cpu()).max() < 1e-6, (prec, kind)
