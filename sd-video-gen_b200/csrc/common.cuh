@@ -42,6 +42,12 @@ struct Epilogue {
   int out_clip_rows = 0, out_row_off = 0;
   // residual read with the same clip-strided addressing when res_clip_rows > 0
   int res_clip_rows = 0, res_row_off = 0;
+  // deferred LayerNorm of the residual: when ln_stats != nullptr, `residual` holds the PRE-norm sums y and the
+  // value added is (y - mean[row]) * rstd[row] * ln_w[col] + ln_b[col], i.e. LayerNorm(y) recomputed on the fly
+  // from the row statistics the LayerNorm kernel left behind (it then does not have to write its fp32 output)
+  const float2* ln_stats = nullptr;
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
 };
 
 __device__ __forceinline__ int epi_out_row(const Epilogue& e, int row) {
@@ -71,7 +77,15 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, float acc, int row
   v *= e.alpha;
   if (pe_row >= 0) v += __ldg(e.pe + static_cast<size_t>(pe_row) * e.ld_pe + col);
   if (e.relu) v = fmaxf(v, 0.0f);
-  if (e.residual) v += __ldg(e.residual + static_cast<size_t>(epi_res_row(e, row)) * e.ld_res + col);
+  if (e.residual) {
+    const int rrow = epi_res_row(e, row);
+    float r = __ldg(e.residual + static_cast<size_t>(rrow) * e.ld_res + col);
+    if (e.ln_stats) {
+      const float2 st = __ldg(e.ln_stats + rrow);
+      r = (r - st.x) * st.y * __ldg(e.ln_w + col) + __ldg(e.ln_b + col);
+    }
+    v += r;
+  }
   return v;
 }
 

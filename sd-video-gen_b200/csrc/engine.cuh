@@ -110,6 +110,8 @@ class Engine {
   float* c_qkv_d = nullptr;  // [max_clips * max_history][3d]
   bool use_cache = true;
   bool use_prune = true;     // last-decoder-layer pruning in rollouts (SDVG_PRUNE=0 disables)
+  bool lazy_ln = true;       // deferred LayerNorm of the residual stream (SDVG_LAZY_LN=0 disables), see ResSrc
+  float2* ln_stats = nullptr;  // [max_rows] (mean, rstd) left behind by the last LayerNorm kernel
   int* pe_mod64 = nullptr;   // [max_clips] b mod 64
 
   struct TimedSpan { cudaEvent_t a, b; int cls; double flops, bytes; };
@@ -369,6 +371,8 @@ class Engine {
                         (e = dalloc(&c_qkv_d, slots_total * 3 * d)) != cudaSuccess))
         return fail_cuda(e, "cache alloc");
     }
+    if (const char* v = std::getenv("SDVG_LAZY_LN")) lazy_ln = std::atoi(v) != 0;
+    if ((e = dalloc(&ln_stats, static_cast<size_t>(max_rows))) != cudaSuccess) return fail_cuda(e, "stats alloc");
     std::vector<int> mod(c.max_clips);
     for (int i = 0; i < c.max_clips; ++i) mod[i] = i % 64;
     if ((e = dalloc(&pe_mod64, static_cast<size_t>(c.max_clips))) != cudaSuccess) return fail_cuda(e, "pe alloc");
@@ -549,8 +553,9 @@ class Engine {
   }
 
   cudaError_t layernorm(const ActBuf& in, int rows, const LNParam& n1, const LNParam* n2, const ActBuf& dst,
-                        bool want_f32, int rows_per_clip, int first_token, cudaStream_t st) {
+                        bool want_f32, int rows_per_clip, int first_token, cudaStream_t st, float2* stats = nullptr) {
     LnArgs a{};
+    a.stats = stats;
     a.x = in.f32; a.ldx = in.ld32; a.rows = rows; a.d = cfg.dim_model;
     a.w1 = n1.w; a.b1 = n1.b; a.w2 = n2 ? n2->w : nullptr; a.b2 = n2 ? n2->b : nullptr;
     a.eps = cfg.layer_norm_eps;
@@ -690,6 +695,19 @@ class Engine {
   // n_new positions); cache rows of clip b are slots [b*Hn, (b+1)*Hn), the window starts at slot `first`.
   struct CacheStep { int Hn, first, n_new; };
 
+  // Where a sub-layer's residual comes from.  Plain: the fp32 stream rows.  Deferred (stats != nullptr): the
+  // pre-norm sums left in ybuf by the previous sub-layer plus the row statistics and affine parameters of the
+  // LayerNorm that turned them into the current stream - the consuming GEMM epilogue recomputes LayerNorm(y) for
+  // the elements it adds, so that LayerNorm kernel only writes the 16-bit operand planes and 8 bytes per row
+  // instead of a second fp32 copy of the stream (LayerNorm was HBM-bound: 10 -> 6 bytes per element).
+  struct ResSrc {
+    const float* ptr = nullptr; int ld = 0;
+    const float2* stats = nullptr; const float* w = nullptr; const float* b = nullptr;
+  };
+  static void residual_from(Epilogue& e, const ResSrc& rs) {
+    e.residual = rs.ptr; e.ld_res = rs.ld; e.ln_stats = rs.stats; e.ln_w = rs.w; e.ln_b = rs.b;
+  }
+
   cudaError_t run_model(int B, int Ss, int St, bool same, int mask_kind, const float* mask, const int* pe_index,
                         Epilogue oe, cudaStream_t st, const CacheStep* cs = nullptr) {
     const int d = cfg.dim_model;
@@ -704,8 +722,18 @@ class Engine {
       return gemm(lat, embedding, B * S, e, st);
     };
     const int hd = d / cfg.num_heads;
-    auto self_attention = [&](const ActBuf& x, const AttnWeights& w, int S, int M, int mk, const float* mptr,
-                              const LNParam& norm, const ActBuf& x_out, bool first_layer) -> cudaError_t {
+    const bool lazy = lazy_ln && tc();
+    // LayerNorm of ybuf into the stream buffer `x_out`; returns how the next sub-layer reads its residual
+    auto norm_to = [&](int M, int S, const LNParam& norm, const ActBuf& x_out, bool allow_lazy, ResSrc& out_rs) -> cudaError_t {
+      if (lazy && allow_lazy) {
+        out_rs = ResSrc{ybuf.f32, ybuf.ld32, ln_stats, norm.w, norm.b};
+        return layernorm(ybuf, M, norm, nullptr, x_out, false, S, 0, st, ln_stats);
+      }
+      out_rs = ResSrc{x_out.f32, x_out.ld32, nullptr, nullptr, nullptr};
+      return layernorm(ybuf, M, norm, nullptr, x_out, true, S, 0, st);
+    };
+    auto self_attention = [&](const ActBuf& x, ResSrc& rs, const AttnWeights& w, int S, int M, int mk, const float* mptr,
+                              const LNParam& norm, const ActBuf& x_out, bool first_layer, bool allow_lazy) -> cudaError_t {
       Epilogue e;
       if (qkv16 && !first_layer && attention16_supported(hd, S, S, mk)) {
         e.out_hi = qkv16; e.ld16 = 3 * d;   // Q|K|V straight to 16-bit planes
@@ -719,27 +747,31 @@ class Engine {
         SDVG_CK(attention(qkv.f32, 3 * d, qkv.f32 + d, qkv.f32 + 2 * d, 3 * d, B, S, S, mk, mptr, 0, attn, st));
       }
       Epilogue eo;
-      eo.residual = x.f32; eo.ld_res = x.ld32;
+      residual_from(eo, rs);
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
       SDVG_CK(gemm(attn, w.out, M, eo, st));
-      return layernorm(ybuf, M, norm, nullptr, x_out, true, S, 0, st);
+      return norm_to(M, S, norm, x_out, allow_lazy, rs);
     };
-    auto ffn = [&](const ActBuf& x, const Linear& l1, const Linear& l2, int M, int S, const LNParam& norm,
-                   const LNParam* chained, const ActBuf& x_out, bool want_f32) -> cudaError_t {
+    auto ffn = [&](const ActBuf& x, ResSrc& rs, const Linear& l1, const Linear& l2, int M, int S, const LNParam& norm,
+                   const LNParam* chained, const ActBuf& x_out, bool allow_lazy) -> cudaError_t {
       Epilogue e1;
       e1.relu = 1;
       out_to(e1, ffh, !tc());
       SDVG_CK(gemm(x, l1, M, e1, st));
       Epilogue e2;
-      e2.residual = x.f32; e2.ld_res = x.ld32;
+      residual_from(e2, rs);
       out_to(e2, ybuf, true); e2.out_hi = nullptr; e2.out_lo = nullptr;
       SDVG_CK(gemm(ffh, l2, M, e2, st));
-      return layernorm(ybuf, M, norm, chained, x_out, want_f32, S, 0, st);
+      if (chained) {  // last layer of a stack: norm chained with the stack's final norm, operand planes only
+        rs = ResSrc{};
+        return layernorm(ybuf, M, norm, chained, x_out, false, S, 0, st);
+      }
+      return norm_to(M, S, norm, x_out, allow_lazy, rs);
     };
 
     // layer-0 self-attention from the token-local caches (cs != nullptr): only the new tokens go through the
     // embedding and the layer-0 QKV GEMMs; attention and the out-proj residual read the cached rows by slot
-    auto self_attention_cached = [&](float* c_qkv, const AttnWeights& w, int S, int M, int mk,
+    auto self_attention_cached = [&](float* c_qkv, ResSrc& rs, const AttnWeights& w, int S, int M, int mk,
                                      const LNParam& norm, const ActBuf& x_out) -> cudaError_t {
       Epilogue e;  // new tokens' Q/K/V -> cache rows (clip b, slot first + S - n_new + j)
       e.rows_per_clip = cs->n_new; e.row_map = 3; e.out_clip_rows = cs->Hn; e.out_row_off = cs->first + S - cs->n_new;
@@ -752,7 +784,7 @@ class Engine {
       eo.residual = c_emb; eo.ld_res = d; eo.rows_per_clip = S; eo.res_clip_rows = cs->Hn; eo.res_row_off = cs->first;
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
       SDVG_CK(gemm(attn, w.out, M, eo, st));
-      return layernorm(ybuf, M, norm, nullptr, x_out, true, S, 0, st);
+      return norm_to(M, S, norm, x_out, true, rs);
     };
 
     // ---------------- encoder
@@ -772,11 +804,12 @@ class Engine {
       SDVG_CK(embed(lat_s, Ss, emb_s));
     }
     const ActBuf* x = &emb_s;
+    ResSrc rs{emb_s.f32, emb_s.ld32, nullptr, nullptr, nullptr};
     for (int l = 0; l < Le; ++l) {
-      if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_e, enc[l].sa, Ss, Ms, 0, enc[l].n1, xs));
-      else SDVG_CK(self_attention(*x, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs, l == 0));
+      if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_e, rs, enc[l].sa, Ss, Ms, 0, enc[l].n1, xs));
+      else SDVG_CK(self_attention(*x, rs, enc[l].sa, Ss, Ms, 0, nullptr, enc[l].n1, xs, l == 0, true));
       const bool last = (l == Le - 1);
-      SDVG_CK(ffn(xs, enc[l].ff1, enc[l].ff2, Ms, Ss, enc[l].n2, last ? &enc_norm : nullptr, last ? mem : xs, !last));
+      SDVG_CK(ffn(xs, rs, enc[l].ff1, enc[l].ff2, Ms, Ss, enc[l].n2, last ? &enc_norm : nullptr, last ? mem : xs, true));
       x = &xs;
     }
     if (Le == 0) SDVG_CK(layernorm(emb_s, Ms, enc_norm, nullptr, mem, false, Ss, 0, st));
@@ -784,6 +817,7 @@ class Engine {
     // ---------------- decoder
     const ActBuf* y = &emb_s;
     if (!same) { SDVG_CK(embed(lat_t, St, emb_t)); y = &emb_t; }
+    rs = ResSrc{y->f32, y->ld32, nullptr, nullptr, nullptr};
     // Exact pruning of the last decoder layer (rollout only keeps the last token, prediction/predict.py:42): its
     // self-attention K/V need every row, but Q, both out-projections, the cross-attention query, the FFN, the
     // final norms and the output projection are computed for the last token of each clip only (M = B rows).
@@ -793,8 +827,8 @@ class Engine {
         SDVG_CK(pruned_last_layer(dec[l], B, Ss, St, mask_kind, mask, oe, st));
         return cudaSuccess;
       }
-      if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_d, dec[l].sa, St, Mt, mask_kind, dec[l].n1, xt));
-      else SDVG_CK(self_attention(*y, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt, l == 0));
+      if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_d, rs, dec[l].sa, St, Mt, mask_kind, dec[l].n1, xt));
+      else SDVG_CK(self_attention(*y, rs, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt, l == 0, true));
       // cross attention: Q from the target stream, K/V from the encoder memory
       Epilogue eq, ekv;
       if (qkv16 && attention16_supported(hd, St, Ss, 0)) {
@@ -812,12 +846,14 @@ class Engine {
         SDVG_CK(attention(qc.f32, d, kvc.f32, kvc.f32 + d, 2 * d, B, St, Ss, 0, nullptr, 0, attn, st));
       }
       Epilogue eo;
-      eo.residual = xt.f32; eo.ld_res = xt.ld32;
+      residual_from(eo, rs);
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
       SDVG_CK(gemm(attn, dec[l].ca.out, Mt, eo, st));
-      SDVG_CK(layernorm(ybuf, Mt, dec[l].n2, nullptr, xt, true, St, 0, st));
+      SDVG_CK(norm_to(Mt, St, dec[l].n2, xt, true, rs));
       const bool last = (l == Ld - 1);
-      SDVG_CK(ffn(xt, dec[l].ff1, dec[l].ff2, Mt, St, dec[l].n3, last ? &dec_norm : nullptr, last ? fin : xt, !last));
+      // the pruned last layer gathers fp32 rows of its input stream, so the layer before it writes them
+      const bool feeds_pruned = prune && l == Ld - 2;
+      SDVG_CK(ffn(xt, rs, dec[l].ff1, dec[l].ff2, Mt, St, dec[l].n3, last ? &dec_norm : nullptr, last ? fin : xt, !feeds_pruned));
       y = &xt;
     }
     if (Ld == 0) SDVG_CK(layernorm(*y, Mt, dec_norm, nullptr, fin, false, St, 0, st));

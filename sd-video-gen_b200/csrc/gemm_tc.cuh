@@ -111,16 +111,22 @@ template <int PF>
 struct EpiPre {
   float4 b4[PF];
   float4 res[PF][8];
+  float4 lw[PF], lb[PF];  // deferred-LayerNorm weights of the chunk's columns (Epilogue::ln_stats mode)
+  float2 st[8];           // (mean, rstd) of this lane's 8 rows of the tile
 };
 
 template <bool FANCY>
 __device__ __forceinline__ void epi_prefetch_chunk(const TcGemmArgs& args, int row0, int col, int lr, float4& b4,
-                                                   float4 (&res)[8]) {
+                                                   float4 (&res)[8], float4& lw, float4& lb) {
   const Epilogue& e = args.epi;
   const int rows_valid = args.M - row0;
   b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < args.N) {
     if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    if (e.ln_stats) {
+      lw = __ldg(reinterpret_cast<const float4*>(e.ln_w + col));
+      lb = __ldg(reinterpret_cast<const float4*>(e.ln_b + col));
+    }
     if (e.residual) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -140,9 +146,18 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmArgs& args, int
                                                      EpiPre<PF>& pre) {
   if (!args.vec4) return;
   const int lr = lane >> 3, lc = (lane & 7) * 4;
+  if (args.epi.ln_stats) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + i * 4 + lr;
+      int rrow = row;
+      if constexpr (FANCY) rrow = epi_res_row(args.epi, row);
+      pre.st[i] = row < args.M ? __ldg(args.epi.ln_stats + rrow) : make_float2(0.f, 0.f);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < (NCW < PF ? NCW : PF); ++j)
-    epi_prefetch_chunk<FANCY>(args, row0, col_base + (c0 + j) * 32 + lc, lr, pre.b4[j], pre.res[j]);
+    epi_prefetch_chunk<FANCY>(args, row0, col_base + (c0 + j) * 32 + lc, lr, pre.b4[j], pre.res[j], pre.lw[j], pre.lb[j]);
 }
 
 // Epilogue of one accumulator tile for one warp: 32 TMEM lanes (rows row0..row0+31) x NCW chunks of 32 columns
@@ -231,6 +246,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
       __syncwarp();
     }
     const float4 b4 = pre.b4[j % PF];
+    const float4 lw = pre.lw[j % PF], lb = pre.lb[j % PF];
+    const bool ln_res = e.ln_stats != nullptr;
     const int col = col_base + c * 32 + lc;
     if (col < N) {
 #pragma unroll
@@ -257,7 +274,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
           }
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           if (residual) {
-            const float4 rv = pre.res[j % PF][i];
+            float4 rv = pre.res[j % PF][i];
+            if (ln_res) {  // LayerNorm of the pre-norm sums, recomputed from the row statistics
+              const float2 st = pre.st[i];
+              rv.x = (rv.x - st.x) * st.y * lw.x + lb.x; rv.y = (rv.y - st.x) * st.y * lw.y + lb.y;
+              rv.z = (rv.z - st.x) * st.y * lw.z + lb.z; rv.w = (rv.w - st.x) * st.y * lw.w + lb.w;
+            }
             v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
           }
           if (out32 && out_row >= 0) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(out_row) * ld32 + col) = v;
@@ -272,7 +294,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
     }
     // this slot is free again: start the loads of chunk j + PF of this tile
     if (j + PF < NCW)
-      epi_prefetch_chunk<FANCY>(args, row0, col_base + (c + PF) * 32 + lc, lr, pre.b4[j % PF], pre.res[j % PF]);
+      epi_prefetch_chunk<FANCY>(args, row0, col_base + (c + PF) * 32 + lc, lr, pre.b4[j % PF], pre.res[j % PF],
+                                pre.lw[j % PF], pre.lb[j % PF]);
     __syncwarp();
   }
 }
@@ -403,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int half = (warp - 2) >> 2;     // which half of the tile's column chunks
     constexpr int kChunks = BN / 32;
     constexpr int NCW = Cfg::kEpiActive == 8 ? kChunks / 2 : kChunks;   // chunks per participating warp
-    constexpr int PF = NCW < 3 ? NCW : 3;
+    constexpr int PF = NCW < 2 ? NCW : 2;
     const bool active = Cfg::kEpiActive == 8 || half == 0;
     const int c0 = Cfg::kEpiActive == 8 ? half * NCW : 0;
     float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
@@ -469,6 +492,7 @@ inline bool epilogue_vec4_ok(const Epilogue& e, int N) {
   if (e.bias && !al(e.bias, 16)) return false;
   if (e.pe && (!al(e.pe, 16) || e.ld_pe % 4 != 0)) return false;
   if (e.residual && (!al(e.residual, 16) || e.ld_res % 4 != 0)) return false;
+  if (e.ln_stats && (!al(e.ln_stats, 8) || !al(e.ln_w, 16) || !al(e.ln_b, 16))) return false;
   if (e.out32 && (!al(e.out32, 16) || e.ld32 % 4 != 0)) return false;
   if (e.out_hi && (!al(e.out_hi, 8) || e.ld16 % 4 != 0)) return false;
   if (e.out_lo && !al(e.out_lo, 8)) return false;

@@ -184,7 +184,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int NCW = BN / 64;              // 32-column chunks per warp
-    constexpr int PF = NCW < 3 ? NCW : 3;     // chunks whose bias / residual operands are loaded ahead
+    constexpr int PF = NCW < 2 ? NCW : 2;     // chunks whose bias / residual operands are loaded ahead (3 spills registers)
     const int c0 = half * NCW;
     float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
     int buf = 0;

@@ -20,11 +20,12 @@ struct LnArgs {
   int rows_per_clip, first_token, compact;
   float* out32; int ld32;
   uint16_t* out_hi; uint16_t* out_lo; int ld16; int bf16;
+  float2* stats;  // optional [rows]: (mean, rstd) of the first LayerNorm, indexed like the output rows (deferred residual)
 };
 
 template <int NV>
-__device__ __forceinline__ void ln_inplace(float4 (&v)[NV], int d, int lane, const float* __restrict__ w,
-                                           const float* __restrict__ b, float eps) {
+__device__ __forceinline__ float2 ln_inplace(float4 (&v)[NV], int d, int lane, const float* __restrict__ w,
+                                             const float* __restrict__ b, float eps) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -56,6 +57,7 @@ __device__ __forceinline__ void ln_inplace(float4 (&v)[NV], int d, int lane, con
       v[i].w = (v[i].w - mean) * rstd * ww.w + bb.w;
     }
   }
+  return make_float2(mean, rstd);
 }
 
 template <int NV>
@@ -76,7 +78,8 @@ __global__ void __launch_bounds__(128, NV <= 16 ? 4 : 2) layernorm_kernel(const 
     const int c = (i * 32 + lane) * 4;
     v[i] = c < a.d ? *reinterpret_cast<const float4*>(a.x + in_row * a.ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  ln_inplace<NV>(v, a.d, lane, a.w1, a.b1, a.eps);
+  const float2 st1 = ln_inplace<NV>(v, a.d, lane, a.w1, a.b1, a.eps);
+  if (a.stats && lane == 0) a.stats[out_row] = st1;
   if (a.w2) ln_inplace<NV>(v, a.d, lane, a.w2, a.b2, a.eps);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(128) layernorm_block_kernel(const __grid_const
       q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     }
     const float rstd = rsqrtf(block_sum_128(q, red, lane, warp) * inv_d + a.eps);
+    if (pass == 0 && a.stats && tid == 0) a.stats[out_row] = make_float2(mean, rstd);
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = (i * 128 + tid) * 4;
