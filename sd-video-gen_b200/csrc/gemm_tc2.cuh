@@ -223,12 +223,14 @@ inline cudaError_t launch_gemm_tc2_f(const CUtensorMap& a_hi, const CUtensorMap&
                                      const CUtensorMap& b_lo, const TcGemmArgs& args, int num_sms,
                                      cudaStream_t stream) {
   using Cfg = Tc2Cfg<BN, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, SPLIT, FANCY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   const int tiles = ceil_div(args.M, kTc2BM) * ceil_div(args.N, BN);
   const int pairs = num_sms / 2;
