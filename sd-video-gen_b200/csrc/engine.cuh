@@ -176,8 +176,13 @@ class Engine {
   bool map_planes(Planes& p, bool weight) {
     // lo planes are always fp16; hi planes follow the mode
     if (!weight) {
-      if (!make_tmap_2d(&p.tm_hi[0], p.hi, p.rows, p.ld, p.ld, kTcBM, bf16())) return false;
-      if (p.lo && !make_tmap_2d(&p.tm_lo[0], p.lo, p.rows, p.ld, p.ld, kTcBM, false)) return false;
+      // slot 0: 128-row boxes (the tile height); slots 1, 2: 64- and 32-row boxes for small-M GEMMs, which
+      // would otherwise stream 128 rows of A per K block to use 40 of them (a_box_slot)
+      for (int s = 0; s < 3; ++s) {
+        const int box = kTcBM >> s;
+        if (!make_tmap_2d(&p.tm_hi[s], p.hi, p.rows, p.ld, p.ld, box, bf16())) return false;
+        if (p.lo && !make_tmap_2d(&p.tm_lo[s], p.lo, p.rows, p.ld, p.ld, box, false)) return false;
+      }
       return true;
     }
     for (int i = 0; i < kNumBoxes; ++i) {
@@ -495,12 +500,18 @@ class Engine {
     return best;
   }
 
-  cudaError_t gemm_tc_dispatch(const Planes& A, const Planes& B, bool split, TilePlan plan, const TcGemmArgs& args,
+  // A-operand TMA box height for the one-CTA kernel: 128 rows, or 64 / 32 when the whole problem has fewer rows
+  static int a_box_slot(int M) { return M <= 32 ? 2 : M <= 64 ? 1 : 0; }
+
+  cudaError_t gemm_tc_dispatch(const Planes& A, const Planes& B, bool split, TilePlan plan, const TcGemmArgs& args_in,
                                cudaStream_t st) {
+    TcGemmArgs args = args_in;
+    args.a_box_rows = plan.pair ? kTcBM : (kTcBM >> a_box_slot(args.M));
     const int bn = plan.bn;
     const int bi = box_index(plan.pair ? bn / 2 : bn);
-    const CUtensorMap& ah = A.tm_hi[0];
-    const CUtensorMap& al = split ? A.tm_lo[0] : A.tm_hi[0];
+    const int as = plan.pair ? 0 : a_box_slot(args.M);
+    const CUtensorMap& ah = A.tm_hi[as];
+    const CUtensorMap& al = split ? A.tm_lo[as] : A.tm_hi[as];
     const CUtensorMap& bh = B.tm_hi[bi];
     const CUtensorMap& bl = split ? B.tm_lo[bi] : B.tm_hi[bi];
     if (plan.pair) {
@@ -540,7 +551,7 @@ class Engine {
     }
     const bool split = L.split && A.p.lo != nullptr;
     const TilePlan plan = choose_plan(M, L.N, split);
-    TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, 0, nullptr, e};
+    TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, kTcBM, 0, nullptr, e};
     const double planes = split ? 2.0 : 1.0;
     Scope sc(this, KC_GEMM_TC, flops, 2.0 * planes * (double(M) * L.K + double(L.N) * L.K) + 4.0 * double(M) * L.N, st);
     return gemm_tc_dispatch(A.p, L.p, split, plan, args, st);

@@ -63,6 +63,7 @@ struct TcGemmArgs {
   int M, N, K;
   int bf16;  // operand format of the hi planes
   int vec4;  // all epilogue pointers / pitches are 16-byte aligned and N % 4 == 0 (set by the launcher)
+  int a_box_rows;             // rows of A the TMA loads per K block (128, or 64 / 32 for small-M problems; one-CTA kernel)
   int max_stages;             // 0 = all smem stages; >0 caps the TMA ring depth (pipeline experiments, SDVG_STAGES)
   unsigned long long* trace;  // optional [64] device buffer: CTA 0 records %globaltimer at pipeline events (tools/gemm_trace.py)
   Epilogue epi;
@@ -361,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    const uint32_t a_box_bytes = static_cast<uint32_t>((args.a_box_rows > 0 ? args.a_box_rows : kTcBM) * kTcBK * 2);
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -370,7 +372,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
         uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          // rows of the smem A tile beyond a_box_rows keep stale bits: they only feed accumulator rows >= M,
+          // which the epilogue never stores
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kPlanes * (a_box_bytes + Cfg::kBBytes));
           ptx::tma_load_2d(sp, &tmA_hi, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
           if (SPLIT) ptx::tma_load_2d(sp + Cfg::kABytes, &tmA_lo, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
           ptx::tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kTcBK, n_blk * BN);

@@ -164,10 +164,14 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     Planes pa, pb;
     const int box = plan.pair ? bn / 2 : (bn > N ? N : bn);
     const int bi = box_index(plan.pair ? bn / 2 : bn);
-    ok = make_tmap_2d(&pa.tm_hi[0], a_hi, Mp, Kp, Kp, kTcBM, bf) && make_tmap_2d(&pb.tm_hi[bi], w_hi, N, Kp, Kp, box, bf);
-    if (ok && split) ok = make_tmap_2d(&pa.tm_lo[0], a_lo, Mp, Kp, Kp, kTcBM, false) && make_tmap_2d(&pb.tm_lo[bi], w_lo, N, Kp, Kp, box, false);
+    ok = make_tmap_2d(&pb.tm_hi[bi], w_hi, N, Kp, Kp, box, bf);
+    if (ok && split) ok = make_tmap_2d(&pb.tm_lo[bi], w_lo, N, Kp, Kp, box, false);
+    for (int s = 0; s < 3 && ok; ++s) {
+      ok = make_tmap_2d(&pa.tm_hi[s], a_hi, Mp, Kp, Kp, kTcBM >> s, bf);
+      if (ok && split) ok = make_tmap_2d(&pa.tm_lo[s], a_lo, Mp, Kp, Kp, kTcBM >> s, false);
+    }
     if (!ok) { cleanup(); g_create_error = "sdvg_gemm: cuTensorMapEncodeTiled failed"; return SDVG_ERR_CUDA; }
-    TcGemmArgs args{M, N, K, bf ? 1 : 0, 0, 0, nullptr, e};
+    TcGemmArgs args{M, N, K, bf ? 1 : 0, 0, kTcBM, 0, nullptr, e};
     if (const char* sv = std::getenv("SDVG_STAGES")) args.max_stages = std::atoi(sv);
     // SDVG_TRACE_BUF=<device pointer to 64 uint64> : pipeline timestamps of CTA 0 (tools/gemm_trace.py)
     if (const char* tb = std::getenv("SDVG_TRACE_BUF")) args.trace = reinterpret_cast<unsigned long long*>(std::strtoull(tb, nullptr, 0));
