@@ -10,6 +10,7 @@
 // 2 additive fp32 (Sq x Sk) as passed to forward(..., tgt_mask).
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace sdvg {
 
@@ -475,6 +476,179 @@ __global__ void __launch_bounds__(128) attention_exact16_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core variant for 16-bit Q/K/V planes, head dim 256, Sq <= 8, Sk <= 8 (the rollout's 5- and 6-token
+// windows and the pruned last layer's single query).  The warp-level kernels above are issue-bound (ncu r1b:
+// ~1850 instructions per (clip, head), 54 % issue utilisation, DRAM 27 %); here the two products run on
+// mma.sync.m16n8k16 (legacy tensor path - the tiles are 5x5x256, far too small for tcgen05):
+//   S = Q K^T : A = Q (rows padded to 16 by aliasing), B = K ([key][hd] rows are the "col" operand as stored)
+//   O^T = V^T P^T : A = V^T through ldmatrix.trans, B = P^T - which is exactly the score accumulator fragment
+//                   each thread already holds (row q = lane/4, keys 2t, 2t+1), so no shuffles are needed
+// Softmax runs on the accumulator fragments in fp32 (row reductions across the 4 lanes of a quad); P is rounded
+// to the plane format for the second product.  One warp per (clip, head), operands staged in padded smem by
+// cp.async (rows of 512 B + 16 B pad: ldmatrix conflict-free), output staged through smem for 16-byte stores.
+inline bool& attention_mma_enabled() { static bool on = true; return on; }  // SDVG_ATTN_MMA=0 disables
+constexpr int kMmaHd = 256;
+constexpr int kMmaRow = kMmaHd + 8;   // halves per smem row
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+template <bool BF16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+struct AttnMmaSmem {                       // per warp
+  uint16_t q[8][kMmaRow];                  // query rows (reused for the output rows)
+  uint16_t k[8][kMmaRow];
+  uint16_t v[9][kMmaRow];                  // row 8 = zeros: every key row >= Sk points here
+};
+
+template <bool BF16, int MASK>
+__global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constant__ AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  constexpr float kLog2e = 1.4426950408889634f;
+  pdl_wait();
+  pdl_trigger();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * 4 + wib;
+  if (warp_global >= a.clips * a.heads) return;
+  const int b = warp_global / a.heads, h = warp_global - b * a.heads;
+  AttnMmaSmem& sm = reinterpret_cast<AttnMmaSmem*>(attn_smem)[wib];
+  const int Sq = a.Sq, Sk = a.Sk;
+  const uint16_t* qb = reinterpret_cast<const uint16_t*>(a.q) + static_cast<size_t>(b) * a.q_clip_stride + h * kMmaHd;
+  const uint16_t* kb = reinterpret_cast<const uint16_t*>(a.k) + static_cast<size_t>(b) * a.kv_clip_stride + h * kMmaHd;
+  const uint16_t* vb = reinterpret_cast<const uint16_t*>(a.v) + static_cast<size_t>(b) * a.kv_clip_stride + h * kMmaHd;
+
+  // ---- stage Q, K, V rows (512 B each: 32 lanes x 16 B) and the zero row
+  for (int r = a.q_first; r < Sq; ++r) cp_async16(ptx::smem_u32(&sm.q[r][lane * 8]), qb + static_cast<size_t>(r) * a.ldq + lane * 8);
+  for (int r = 0; r < Sk; ++r) {
+    cp_async16(ptx::smem_u32(&sm.k[r][lane * 8]), kb + static_cast<size_t>(r) * a.ldkv + lane * 8);
+    cp_async16(ptx::smem_u32(&sm.v[r][lane * 8]), vb + static_cast<size_t>(r) * a.ldkv + lane * 8);
+  }
+  *reinterpret_cast<uint4*>(&sm.v[8][lane * 8]) = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  // ---- S = Q K^T  (16 x 8 tile, rows 8..15 alias rows 0..7 and are ignored)
+  const int mid = lane >> 3, mr = lane & 7;           // ldmatrix: matrix id, row inside the matrix
+  const uint32_t q_addr = ptx::smem_u32(&sm.q[mr][(mid >> 1) * 8]);      // A: M0 rows0-7 k0-7 | M1 rows8-15(alias) k0-7 | M2 k8-15 | M3
+  const uint32_t k_addr = ptx::smem_u32(&sm.k[mr][(mid & 1) * 8]);       // B (x2, lanes 0-15): n rows, k 0-7 | k 8-15
+  float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kk = 0; kk < kMmaHd / 16; ++kk) {
+    uint32_t af[4], bf[2];
+    ldmatrix_x4(af, q_addr + kk * 32);
+    ldmatrix_x2(bf, k_addr + kk * 32);
+    mma_16816<BF16>(sc, af, bf);
+  }
+  // ---- softmax over the keys of row g = lane / 4 (this thread holds keys 2t, 2t+1)
+  const int g = lane >> 2, t = lane & 3;
+  const float scale2 = a.scale * kLog2e;
+  float p0 = sc[0] * scale2, p1 = sc[1] * scale2;
+  const int j0 = 2 * t, j1 = 2 * t + 1;
+  const bool row_ok = g >= a.q_first && g < Sq;
+  bool ok0 = row_ok && j0 < Sk, ok1 = row_ok && j1 < Sk;
+  if (MASK == 1) { ok0 = ok0 && j0 <= g + (Sk - Sq); ok1 = ok1 && j1 <= g + (Sk - Sq); }
+  p0 = ok0 ? p0 : -INFINITY;
+  p1 = ok1 ? p1 : -INFINITY;
+  float mx = fmaxf(p0, p1);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  if (mx == -INFINITY) mx = 0.f;                       // rows outside [q_first, Sq): all weights zero, no NaN
+  p0 = exp2f(p0 - mx);
+  p1 = exp2f(p1 - mx);
+  float sum = p0 + p1;
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  p0 *= inv; p1 *= inv;
+  uint32_t pb[2];                                      // B fragment of P^T: keys 2t, 2t+1 of query g | keys 8.. = 0
+  if constexpr (BF16) { const __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1); pb[0] = *reinterpret_cast<const uint32_t*>(&pp); }
+  else { const __half2 pp = __floats2half2_rn(p0, p1); pb[0] = *reinterpret_cast<const uint32_t*>(&pp); }
+  pb[1] = 0u;
+
+  // ---- O^T = V^T P^T : 16 tiles of 16 head elements x 8 queries
+  // A through ldmatrix.trans of V ([key][hd]): M0 keys0-7 hd m0..+7 | M1 keys0-7 hd m0+8.. | M2 keys8-15 | M3 keys8-15
+  const int vrow = (mid >> 1) ? 8 : (mr < Sk ? mr : 8);               // keys >= Sk (and all of 8..15) -> zero row
+  const uint32_t v_addr = ptx::smem_u32(&sm.v[vrow][(mid & 1) * 8]);
+  __syncwarp();                                                       // everyone is done reading sm.q
+  uint16_t* so = &sm.q[0][0];
+#pragma unroll
+  for (int m = 0; m < kMmaHd / 16; ++m) {
+    uint32_t af[4];
+    ldmatrix_x4_trans(af, v_addr + m * 32);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816<BF16>(o, af, pb);
+    // o[0], o[1] = O[q = 2t, 2t+1][hd = 16 m + g];  o[2], o[3] = same queries, hd = 16 m + g + 8
+    const int hd0 = m * 16 + g;
+    if constexpr (BF16) {
+      so[(2 * t) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[0]));
+      so[(2 * t + 1) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[1]));
+      so[(2 * t) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[2]));
+      so[(2 * t + 1) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[3]));
+    } else {
+      so[(2 * t) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[0]));
+      so[(2 * t + 1) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[1]));
+      so[(2 * t) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[2]));
+      so[(2 * t + 1) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[3]));
+    }
+  }
+  __syncwarp();
+  // ---- store the valid query rows, 16 bytes per lane
+  for (int i = a.q_first; i < Sq; ++i) {
+    const size_t row = a.out_compact ? static_cast<size_t>(b) * (Sq - a.q_first) + (i - a.q_first) : static_cast<size_t>(b) * Sq + i;
+    const uint4 v4 = *reinterpret_cast<const uint4*>(&so[i * kMmaRow + lane * 8]);
+    *reinterpret_cast<uint4*>(a.out_hi + row * a.ld16 + h * kMmaHd + lane * 8) = v4;
+  }
+}
+
+// usable when Q/K/V are 16-bit planes, hd == 256, at most 8 queries and keys, plane output without a lo plane
+inline bool attention_mma_supported(const AttnArgs& a) {
+  return a.hd == kMmaHd && a.Sq <= 8 && a.Sk <= 8 && (a.mask_kind == 0 || a.mask_kind == 1) && a.out_hi && !a.out_lo &&
+         !a.out32 && a.ldq % 8 == 0 && a.ldkv % 8 == 0 && a.q_clip_stride % 8 == 0 && a.kv_clip_stride % 8 == 0 && a.ld16 % 8 == 0;
+}
+
+inline cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t stream) {
+  const int grid = ceil_div(a.clips * a.heads, 4);
+  const size_t smem = 4 * sizeof(AttnMmaSmem);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  if (a.bf16) {
+    if (a.mask_kind == 1) return launch_kernel(attention_mma_kernel<true, 1>, dim3(grid), dim3(128), smem, stream, a);
+    return launch_kernel(attention_mma_kernel<true, 0>, dim3(grid), dim3(128), smem, stream, a);
+  }
+  if (a.mask_kind == 1) return launch_kernel(attention_mma_kernel<false, 1>, dim3(grid), dim3(128), smem, stream, a);
+  return launch_kernel(attention_mma_kernel<false, 0>, dim3(grid), dim3(128), smem, stream, a);
+}
+
 // shapes the 16-bit-input kernel is instantiated for (the engine asks before choosing the 16-bit Q/K/V layout)
 inline bool attention16_supported(int hd, int Sq, int Sk, int mask_kind) {
   const bool shape = (Sq == 5 && Sk == 5) || (Sq == 6 && Sk == 6) || (Sq == 10 && Sk == 10) || (Sq == 5 && Sk == 6) ||
@@ -505,6 +679,7 @@ inline cudaError_t launch_attention16(const AttnArgs& a_in, cudaStream_t stream)
   if (!attention16_supported(a.hd, a.Sq, a.Sk, a.mask_kind) || a.ldq % 8 || a.ldkv % 8 || a.q_clip_stride % 8 ||
       a.kv_clip_stride % 8)
     return cudaErrorInvalidValue;
+  if (attention_mma_enabled() && attention_mma_supported(a)) return launch_attention_mma(a, stream);
   const int grid = ceil_div(a.clips * a.heads, 4);
   switch (a.hd) {
     case 256: return launch_attention16_v<8>(a, grid, stream);

@@ -16,6 +16,7 @@ static thread_local std::string g_create_error;
 static void read_env_options() {
   const char* v = std::getenv("SDVG_PDL");
   if (v) sdvg::pdl_enabled() = std::atoi(v) != 0;
+  if (const char* m = std::getenv("SDVG_ATTN_MMA")) sdvg::attention_mma_enabled() = std::atoi(m) != 0;
 }
 
 extern "C" {
