@@ -150,6 +150,17 @@ int64_t sdvg_launch_count(const sdvg_handle* h);
 int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W, const float* bias, int32_t relu,
               float* C, int32_t M, int32_t N, int32_t K, int32_t block_n, int32_t iters, float* ms, void* stream);
 
+/* Replaces the loss evaluation of the reference's validation / training loops - Trainer.criterion
+ * (trainers/trainer.py:88-109) = use_mse*MSE + use_l1*L1 + use_gdl*lambda_gdl*GDL(alpha) (trainers/trainer.py:65-83)
+ * + use_contrastive*lambda_contrastive*BiPatchNCE(temperature) (models/contrastive_loss.py:28-60) - forward values.
+ *   pred, target: device fp32 (P, B, E) sequence-first, E = 4*h*w - the slices pred[-P:], y_expected[-P:] of
+ *   trainers/trainer.py:145,224.  out: device fp32 [5] = total, MSE, L1, GDL, contrastive (all five are always
+ *   computed except the contrastive term when use_contrastive == 0).  Like the reference, use_mse && use_l1 is
+ *   rejected (SDVG_ERR_INVALID).  Asynchronous on `stream`; scratch is cached per device. */
+int sdvg_criterion(int32_t device, const float* pred, const float* target, int32_t P, int32_t B, int32_t h, int32_t w,
+                   int32_t use_mse, int32_t use_l1, int32_t use_gdl, float lambda_gdl, float alpha,
+                   int32_t use_contrastive, float temperature, float lambda_contrastive, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

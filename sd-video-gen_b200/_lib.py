@@ -14,7 +14,7 @@ KERNEL_CLASSES = ("gemm_tc", "gemm_simt", "attention", "layernorm", "pack")
 SYMBOLS = (
     "sdvg_version", "sdvg_last_error", "sdvg_create", "sdvg_destroy", "sdvg_workspace_bytes", "sdvg_set_weight",
     "sdvg_num_weights", "sdvg_weight_key", "sdvg_finalize_weights", "sdvg_forward", "sdvg_rollout",
-    "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm",
+    "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm", "sdvg_criterion",
 )
 
 
@@ -65,6 +65,7 @@ def load(build_if_missing=True):
     lib.sdvg_launch_count.argtypes = [vp]
     lib.sdvg_launch_count.restype = C.c_int64
     lib.sdvg_gemm.argtypes = [i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(f32), vp]
+    lib.sdvg_criterion.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, vp, vp]
     _lib = lib
     return lib
 

@@ -3,6 +3,7 @@
 #include <new>
 
 #include "engine.cuh"
+#include "loss.cuh"
 
 using sdvg::Engine;
 
@@ -191,6 +192,68 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
   }
   cleanup();
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int sdvg_criterion(int32_t device, const float* pred, const float* target, int32_t P, int32_t B, int32_t h, int32_t w,
+                   int32_t use_mse, int32_t use_l1, int32_t use_gdl, float lambda_gdl, float alpha,
+                   int32_t use_contrastive, float temperature, float lambda_contrastive, float* out, void* stream) {
+  using namespace sdvg;
+  if (!pred || !target || !out || P <= 0 || B <= 0 || h <= 0 || w <= 0 || temperature <= 0.f) {
+    g_create_error = "sdvg_criterion: bad argument"; return SDVG_ERR_INVALID;
+  }
+  if (use_mse && use_l1) {  // trainers/trainer.py:107-109: "Invalid loss function combination"
+    g_create_error = "sdvg_criterion: use_mse and use_l1 together is an invalid loss combination in the reference";
+    return SDVG_ERR_INVALID;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "sdvg_criterion: no such CUDA device"; return SDVG_ERR_CUDA; }
+  read_env_options();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // per-device scratch for the two-stage reductions (grown on demand, never freed: a few hundred KB)
+  static double* scratch[64] = {};
+  static size_t scratch_elems[64] = {};
+  const size_t need = static_cast<size_t>(kLossBlocks) * 4 + static_cast<size_t>(P) * B * 2;
+  const int di = device & 63;
+  if (scratch_elems[di] < need) {
+    if (scratch[di]) { cudaStreamSynchronize(st); cudaFree(scratch[di]); }
+    if (cudaMalloc(reinterpret_cast<void**>(&scratch[di]), need * sizeof(double)) != cudaSuccess) {
+      scratch[di] = nullptr; scratch_elems[di] = 0;
+      g_create_error = "sdvg_criterion: out of device memory"; return SDVG_ERR_CUDA;
+    }
+    scratch_elems[di] = need;
+  }
+  const int hw = h * w;
+  if (use_contrastive && static_cast<size_t>(hw) * 32 > 200 * 1024) {
+    g_create_error = "sdvg_criterion: feature map too large for the contrastive kernel"; return SDVG_ERR_UNSUPPORTED;
+  }
+  LossArgs la{};
+  la.x = pred; la.y = target; la.P = P; la.B = B; la.h = h; la.w = w; la.alpha = alpha;
+  la.inv_temperature = 1.0f / temperature;
+  la.partial = scratch[di]; la.nce_partial = scratch[di] + static_cast<size_t>(kLossBlocks) * 4;
+  const long long total = static_cast<long long>(P) * B * 4 * hw;
+  int blocks = static_cast<int>((total + kLossThreads - 1) / kLossThreads);
+  if (blocks > kLossBlocks) blocks = kLossBlocks;
+  cudaError_t err = launch_kernel(loss_elementwise_kernel, dim3(blocks), dim3(kLossThreads), 0, st, la);
+  if (err == cudaSuccess && use_contrastive) {
+    const size_t smem = static_cast<size_t>(hw) * 2 * sizeof(float4);
+    static bool attr_set[64] = {};
+    if (smem > 48 * 1024 && !attr_set[di]) {
+      err = cudaFuncSetAttribute(loss_nce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set[di] = err == cudaSuccess;
+    }
+    const int threads = hw >= 256 ? 256 : (hw >= 128 ? 128 : 64);
+    if (err == cudaSuccess) err = launch_kernel(loss_nce_kernel, dim3(P * B), dim3(threads), smem, st, la);
+  }
+  if (err == cudaSuccess) {
+    LossFinalArgs fa{};
+    fa.partial = la.partial; fa.n_blocks = blocks; fa.nce_partial = la.nce_partial; fa.n_ct = use_contrastive ? P * B : 0;
+    fa.numel = static_cast<double>(total); fa.nce_rows = static_cast<double>(P) * B * hw;
+    fa.use_mse = use_mse != 0; fa.use_l1 = use_l1 != 0; fa.use_gdl = use_gdl != 0; fa.use_nce = use_contrastive != 0;
+    fa.lambda_gdl = lambda_gdl; fa.lambda_nce = lambda_contrastive; fa.out = out;
+    err = launch_kernel(loss_finalize_kernel, dim3(1), dim3(32), 0, st, fa);
+  }
+  if (err != cudaSuccess) { g_create_error = std::string("sdvg_criterion: ") + cudaGetErrorString(err); return SDVG_ERR_CUDA; }
+  return SDVG_OK;
 }
 
 }  // extern "C"

@@ -309,3 +309,41 @@ def test_last_layer_pruning_is_exact(monkeypatch):
     for (flag, prec, kind), v in outs.items():
         if flag == "1":
             assert R.max_rel_per_frame(v.cpu(), outs["0", prec, kind].cpu()).max() < 1e-6, (prec, kind)
+
+
+def test_losses_match_reference_trainer_gpu():
+    """Trainer.criterion / gradient_difference_loss / BiPatchNCE forward values (trainers/trainer.py:65-109,
+    models/contrastive_loss.py) through sdvg_criterion vs the golden values of the unmodified reference."""
+    g = load_golden("losses")
+    close = lambda a, b: abs(float(a) - float(b)) <= 2e-5 * max(1.0, abs(float(b)))
+    for tag in ("f64", "f128", "p1"):
+        x, y = g[f"{tag}.x"].to(DEV), g[f"{tag}.y"].to(DEV)
+        P, B, F = (int(v) for v in g[f"{tag}.shape"])
+        t = sdvg_b200.loss_terms(x, y, alpha=2, temperature=0.07)
+        assert close(t["mse"], g[f"{tag}.mse"]) and close(t["l1"], g[f"{tag}.l1"])
+        assert close(t["gdl"], g[f"{tag}.gdl2"]) and close(t["contrastive"], g[f"{tag}.nce"])
+        assert close(sdvg_b200.gradient_difference_loss(x, y, 1), g[f"{tag}.gdl1"])
+        nce = sdvg_b200.BiPatchNCE(N=B, T=P, h=F // 8, w=F // 8, temperature=0.07)
+        assert close(nce(x.permute(1, 0, 2).reshape(-1, P, 4, F // 8, F // 8), y.permute(1, 0, 2).reshape(-1, P, 4, F // 8, F // 8)),
+                     g[f"{tag}.nce"])
+        assert close(sdvg_b200.criterion(False, True, False, use_contrastive=False)(x, y), g[f"{tag}.crit_l1"])
+        assert close(sdvg_b200.criterion(True, False, True, 1, 2, True, 0.07, 0.1)(x, y), g[f"{tag}.crit_c5"])
+        assert close(sdvg_b200.criterion(False, True, True, 0.5, 1, True, 0.1, 0.0258)(x, y), g[f"{tag}.crit_all"])
+    assert sdvg_b200.criterion(use_mse=True, use_L1=True) is None
+
+
+def test_validation_step_matches_reference_loop():
+    """One validation_loop iteration (trainers/trainer.py:203-224): S_src = T+1 (with SOS), S_tgt = T, causal mask,
+    loss on the last frames - vs the reference model + the oracle's loss restatement."""
+    from oracle import losses as L
+    g = load_golden("small_rollout")
+    m, ref = ours_from(g, "fp32")
+    frames = torch.randn(4, 5, 256, generator=torch.Generator().manual_seed(31)) * sdvg_b200.LATENT_SCALE
+    batch = torch.cat([torch.full((4, 1, 256), sdvg_b200.SOS_VALUE), frames], 1)           # encode_batch(use_sos=True)
+    with torch.no_grad():
+        pred_ref = ref(batch, batch[:, :-1], ref.get_tgt_mask(5))
+        want = L.criterion(True, False, True, 1, 2, True, 0.07, 0.1)(pred_ref[-5:], batch[:, 1:].permute(1, 0, 2)[-5:])
+    loss_fn = sdvg_b200.criterion(True, False, True, 1, 2, True, 0.07, 0.1)
+    loss, pred = sdvg_b200.validation_step(m, batch.to(DEV), 5, loss_fn)
+    assert maxrel(pred, pred_ref) < TOL32
+    assert abs(float(loss) - float(want)) <= 1e-4 * abs(float(want))
