@@ -621,13 +621,158 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constan
   }
 }
 
-// usable when Q/K/V are 16-bit planes, hd == 256, at most 8 queries and keys, plane output without a lo plane
+// Same scheme for 9..16 queries / keys (the window-10 configurations): two key tiles for Q K^T, two query tiles
+// for O^T = V^T P^T (the V^T fragments are shared by both), 2 warps per CTA (26 KB of operands per warp).
+struct AttnMmaSmem16 {                     // per warp
+  uint16_t q[16][kMmaRow];                 // query rows (reused for the output rows)
+  uint16_t k[16][kMmaRow];
+  uint16_t v[17][kMmaRow];                 // row 16 = zeros: every key row >= Sk points here
+};
+
+template <bool BF16, int MASK>
+__global__ void __launch_bounds__(64) attention_mma16_kernel(const __grid_constant__ AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  constexpr float kLog2e = 1.4426950408889634f;
+  pdl_wait();
+  pdl_trigger();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * 2 + wib;
+  if (warp_global >= a.clips * a.heads) return;
+  const int b = warp_global / a.heads, h = warp_global - b * a.heads;
+  AttnMmaSmem16& sm = reinterpret_cast<AttnMmaSmem16*>(attn_smem)[wib];
+  const int Sq = a.Sq, Sk = a.Sk;
+  const uint16_t* qb = reinterpret_cast<const uint16_t*>(a.q) + static_cast<size_t>(b) * a.q_clip_stride + h * kMmaHd;
+  const uint16_t* kb = reinterpret_cast<const uint16_t*>(a.k) + static_cast<size_t>(b) * a.kv_clip_stride + h * kMmaHd;
+  const uint16_t* vb = reinterpret_cast<const uint16_t*>(a.v) + static_cast<size_t>(b) * a.kv_clip_stride + h * kMmaHd;
+  for (int r = a.q_first; r < Sq; ++r) cp_async16(ptx::smem_u32(&sm.q[r][lane * 8]), qb + static_cast<size_t>(r) * a.ldq + lane * 8);
+  for (int r = 0; r < Sk; ++r) {
+    cp_async16(ptx::smem_u32(&sm.k[r][lane * 8]), kb + static_cast<size_t>(r) * a.ldkv + lane * 8);
+    cp_async16(ptx::smem_u32(&sm.v[r][lane * 8]), vb + static_cast<size_t>(r) * a.ldkv + lane * 8);
+  }
+  *reinterpret_cast<uint4*>(&sm.v[16][lane * 8]) = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  // ---- S = Q K^T : 16 queries x 16 keys = two n-tiles
+  const int mid = lane >> 3, mr = lane & 7;
+  const uint32_t q_addr = ptx::smem_u32(&sm.q[(mid & 1) * 8 + mr][(mid >> 1) * 8]);   // M0 rows0-7 k0-7 | M1 rows8-15 k0-7 | M2, M3: k8-15
+  const uint32_t k_addr = ptx::smem_u32(&sm.k[(mid >> 1) * 8 + mr][(mid & 1) * 8]);   // x4: M0 keys0-7 k0-7 | M1 keys0-7 k8-15 | M2 keys8-15 k0-7 | M3 keys8-15 k8-15
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kk = 0; kk < kMmaHd / 16; ++kk) {
+    uint32_t af[4], bf[4];
+    ldmatrix_x4(af, q_addr + kk * 32);
+    ldmatrix_x4(bf, k_addr + kk * 32);
+    const uint32_t b0[2] = {bf[0], bf[1]}, b1[2] = {bf[2], bf[3]};
+    mma_16816<BF16>(s0, af, b0);
+    mma_16816<BF16>(s1, af, b1);
+  }
+  // ---- softmax: rows g (values s0[0..1], s1[0..1]) and g + 8 (s0[2..3], s1[2..3]); keys 2t, 2t+1, 8+2t, 9+2t
+  const int g = lane >> 2, t = lane & 3;
+  const float scale2 = a.scale * kLog2e;
+  uint32_t pb_lo[2], pb_hi[2];   // B fragments of P^T for queries 0-7 and 8-15
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int row = g + half * 8;
+    float p[4] = {s0[half * 2] * scale2, s0[half * 2 + 1] * scale2, s1[half * 2] * scale2, s1[half * 2 + 1] * scale2};
+    const int key[4] = {2 * t, 2 * t + 1, 8 + 2 * t, 9 + 2 * t};
+    const bool row_ok = row >= a.q_first && row < Sq;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bool ok = row_ok && key[i] < Sk;
+      if (MASK == 1) ok = ok && key[i] <= row + (Sk - Sq);
+      p[i] = ok ? p[i] : -INFINITY;
+      mx = fmaxf(mx, p[i]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    if (mx == -INFINITY) mx = 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p[i] = exp2f(p[i] - mx); sum += p[i]; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    uint32_t w0, w1;
+    if constexpr (BF16) {
+      const __nv_bfloat162 a0 = __floats2bfloat162_rn(p[0] * inv, p[1] * inv), a1 = __floats2bfloat162_rn(p[2] * inv, p[3] * inv);
+      w0 = *reinterpret_cast<const uint32_t*>(&a0); w1 = *reinterpret_cast<const uint32_t*>(&a1);
+    } else {
+      const __half2 a0 = __floats2half2_rn(p[0] * inv, p[1] * inv), a1 = __floats2half2_rn(p[2] * inv, p[3] * inv);
+      w0 = *reinterpret_cast<const uint32_t*>(&a0); w1 = *reinterpret_cast<const uint32_t*>(&a1);
+    }
+    if (half == 0) { pb_lo[0] = w0; pb_lo[1] = w1; } else { pb_hi[0] = w0; pb_hi[1] = w1; }
+  }
+  // ---- O^T = V^T P^T
+  const int vkey = (mid >> 1) * 8 + mr;                                    // M0/M1: keys 0-7, M2/M3: keys 8-15
+  const uint32_t v_addr = ptx::smem_u32(&sm.v[vkey < Sk ? vkey : 16][(mid & 1) * 8]);
+  __syncwarp();
+  uint16_t* so = &sm.q[0][0];
+#pragma unroll
+  for (int m = 0; m < kMmaHd / 16; ++m) {
+    uint32_t af[4];
+    ldmatrix_x4_trans(af, v_addr + m * 32);
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816<BF16>(o0, af, pb_lo);   // queries 0-7
+    mma_16816<BF16>(o1, af, pb_hi);   // queries 8-15
+    const int hd0 = m * 16 + g;
+#pragma unroll
+    for (int qt = 0; qt < 2; ++qt) {
+      const float* o = qt ? o1 : o0;
+      const int q0 = qt * 8 + 2 * t;
+      if constexpr (BF16) {
+        so[q0 * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[0]));
+        so[(q0 + 1) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[1]));
+        so[q0 * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[2]));
+        so[(q0 + 1) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[3]));
+      } else {
+        so[q0 * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[0]));
+        so[(q0 + 1) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[1]));
+        so[q0 * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[2]));
+        so[(q0 + 1) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[3]));
+      }
+    }
+  }
+  __syncwarp();
+  for (int i = a.q_first; i < Sq; ++i) {
+    const size_t row = a.out_compact ? static_cast<size_t>(b) * (Sq - a.q_first) + (i - a.q_first) : static_cast<size_t>(b) * Sq + i;
+    const uint4 v4 = *reinterpret_cast<const uint4*>(&so[i * kMmaRow + lane * 8]);
+    *reinterpret_cast<uint4*>(a.out_hi + row * a.ld16 + h * kMmaHd + lane * 8) = v4;
+  }
+}
+
+// usable when Q/K/V are 16-bit planes, hd == 256, at most 16 queries and keys, plane output without a lo plane
 inline bool attention_mma_supported(const AttnArgs& a) {
-  return a.hd == kMmaHd && a.Sq <= 8 && a.Sk <= 8 && (a.mask_kind == 0 || a.mask_kind == 1) && a.out_hi && !a.out_lo &&
+  return a.hd == kMmaHd && a.Sq <= 16 && a.Sk <= 16 && (a.mask_kind == 0 || a.mask_kind == 1) && a.out_hi && !a.out_lo &&
          !a.out32 && a.ldq % 8 == 0 && a.ldkv % 8 == 0 && a.q_clip_stride % 8 == 0 && a.kv_clip_stride % 8 == 0 && a.ld16 % 8 == 0;
 }
 
+inline cudaError_t launch_attention_mma16(const AttnArgs& a, cudaStream_t stream) {
+  const int grid = ceil_div(a.clips * a.heads, 2);
+  const size_t smem = 2 * sizeof(AttnMmaSmem16);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_mma16_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma16_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma16_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma16_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  if (a.bf16) {
+    if (a.mask_kind == 1) return launch_kernel(attention_mma16_kernel<true, 1>, dim3(grid), dim3(64), smem, stream, a);
+    return launch_kernel(attention_mma16_kernel<true, 0>, dim3(grid), dim3(64), smem, stream, a);
+  }
+  if (a.mask_kind == 1) return launch_kernel(attention_mma16_kernel<false, 1>, dim3(grid), dim3(64), smem, stream, a);
+  return launch_kernel(attention_mma16_kernel<false, 0>, dim3(grid), dim3(64), smem, stream, a);
+}
+
 inline cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t stream) {
+  if (a.Sq > 8 || a.Sk > 8) return launch_attention_mma16(a, stream);
   const int grid = ceil_div(a.clips * a.heads, 4);
   const size_t smem = 4 * sizeof(AttnMmaSmem);
   static bool attr_set[64] = {};

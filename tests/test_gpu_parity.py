@@ -273,6 +273,40 @@ def test_other_baseline_architectures_vs_oracle(name):
     assert R.max_rel_per_frame(tf, want).max() < TOL16
 
 
+def test_tensor_core_attention_windows(monkeypatch):
+    """Head dim 256 (d512, H2) in the 16-bit mode routes attention through the mma.sync kernels (<= 8 and <= 16
+    tokens).  Windows 5, 6 (SOS), 10 and 16 against the oracle (teacher-forced, 5e-3) and against the warp-level
+    kernels (SDVG_ATTN_MMA=0) - the two differ only in rounding P to 16 bits."""
+    from oracle.ref_module import RefTransformer
+    torch.manual_seed(5)
+    ref = RefTransformer(0, 512, 2, 1, 2, 0.1, frame_size=64).eval()
+    ctx = torch.randn(9, 16, 256, generator=torch.Generator().manual_seed(22))
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SDVG_ATTN_MMA", flag)
+        m = sdvg_b200.Transformer(0, 512, 2, 1, 2, 0.1, frame_size=64, precision="mixed")
+        m.load_state_dict(ref.state_dict())
+        m = m.eval().to(DEV)
+        for C, W in ((5, 5), (10, 10), (16, 16), (12, 7)):
+            with torch.no_grad():
+                want = R.rollout_ref(ref, ctx[:, :C], 3, W)
+            got = sdvg_b200.rollout(m, ctx[:, :C].contiguous().to(DEV), 3, W, teacher=want.to(DEV)).cpu()
+            assert R.max_rel_per_frame(got, want).max() < TOL16, (flag, C, W)
+            outs[flag, C, W] = got
+        with torch.no_grad():
+            want = R.rollout_faithful(ref, ctx[:, :5], 3)
+        got = sdvg_b200.rollout(m, ctx[:, :5].contiguous().to(DEV), 3, use_sos=True, teacher=want.to(DEV)).cpu()
+        assert R.max_rel_per_frame(got, want).max() < TOL16, flag
+        outs[flag, "sos"] = got
+        with torch.no_grad():
+            fwd = ref(ctx[:, :11], ctx[:, :10], ref.get_tgt_mask(10))
+        o = m(ctx[:, :11].contiguous().to(DEV), ctx[:, :10].contiguous().to(DEV), "causal")
+        assert maxrel(o, fwd) < TOL16, flag
+        outs[flag, "fwd"] = o.cpu()
+    for k in [k[1:] for k in outs if k[0] == "1"]:
+        assert maxrel(outs[("1",) + k], outs[("0",) + k]) < 2e-3, k
+
+
 def test_edge_shapes():
     """Single clip, single token, window longer than the history, maximum batch of the reference (64), 32-token window."""
     g = load_golden("small_rollout")
