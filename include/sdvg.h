@@ -161,6 +161,52 @@ int sdvg_criterion(int32_t device, const float* pred, const float* target, int32
                    int32_t use_mse, int32_t use_l1, int32_t use_gdl, float lambda_gdl, float alpha,
                    int32_t use_contrastive, float temperature, float lambda_contrastive, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Training step - replaces the body of Trainer.train_loop (trainers/trainer.py:123-165): teacher-forced forward
+ * model(new_batch, y_input, tgt_mask) (:141), criterion on the last frames_to_predict positions (:145),
+ * opt.zero_grad(); loss.backward(); opt.step() (:160-162) with opt = Adam(model.parameters(), lr) (:365).
+ * The handle must use a tensor-core precision (SDVG_FP32 for <=1e-4 gradient parity).  Dropout is the identity
+ * (the reference's DROPOUT_P uses torch's RNG stream; parity is defined for dropout_p = 0). */
+typedef struct sdvg_loss_config {   /* arguments of Trainer.criterion, trainers/trainer.py:88 */
+  int32_t frames_to_predict;        /* P: loss over pred[-P:], y_expected[-P:] (:145) */
+  int32_t use_mse, use_l1, use_gdl;
+  float lambda_gdl, alpha;
+  int32_t use_contrastive;
+  float temperature, lambda_contrastive;
+} sdvg_loss_config;
+
+/* Forward with saved activations, criterion and backward pass.
+ *   src (B, S_src, E) = new_batch, tgt (B, S_tgt, E) = y_input, device fp32, clip-major, contiguous (:123-128);
+ *   expected (S_tgt, B, E) = y_expected after its permute(1, 0, 2) (:131-132), device fp32;
+ *   the causal target mask of get_tgt_mask (:136-137) is implied.  losses: device fp32 [5] = total, MSE, L1, GDL,
+ *   contrastive, or NULL.  Gradients of all parameters land unscaled in the flat fp32 vector of
+ *   sdvg_train_gradients (layout = the parameter arena, see sdvg_param_range); every call overwrites them
+ *   (opt.zero_grad() is implied).
+ *   part 0: the whole step.  part 1: forward, criterion and the decoder-side backward - afterwards the gradients in
+ *   [decoder_offset, count) are final, so a data-parallel caller can start their all-reduce while part 2 (target /
+ *   source embedding and encoder backward, gradients in [0, decoder_offset)) runs. */
+int sdvg_train_backward(sdvg_handle* h, const float* src, const float* tgt, const float* expected, int32_t B, int32_t S_src,
+                        int32_t S_tgt, const sdvg_loss_config* loss, const int32_t* pe_index, float* losses, int32_t part,
+                        void* stream);
+
+/* The flat gradient vector (device fp32, `count` elements) and the offset of the decoder-side bucket.  This is the
+ * buffer a data-parallel trainer hands to ncclAllReduce (torch.distributed.all_reduce on a tensor view of it). */
+int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t* decoder_offset);
+
+/* Offset / element count of a state_dict entry inside the flat parameter (and gradient) vector. */
+int sdvg_param_range(const sdvg_handle* h, const char* key, int64_t* offset, int64_t* count);
+
+/* Device pointer to the (S_tgt, B, E) prediction of the last training forward (what train_loop logs from, :164-172). */
+int sdvg_train_prediction(sdvg_handle* h, const float** pred);
+
+/* torch.optim.Adam.step() (betas, eps as given; no weight decay / amsgrad - the reference's defaults) on every
+ * parameter, using grad_mul * gradient (1 / world_size after a sum all-reduce), then rebuilds the operand planes. */
+int sdvg_train_adam_step(sdvg_handle* h, float lr, float beta1, float beta2, float eps, float grad_mul, void* stream);
+
+/* Reads a parameter back (state_dict()[key], for torch.save at trainers/trainer.py:294): `out` is host or device
+ * fp32 with room for the entry.  Synchronises `stream`. */
+int sdvg_get_weight(sdvg_handle* h, const char* key, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

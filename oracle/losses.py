@@ -1,8 +1,9 @@
 """Restatement of the reference's loss functions (TEST INFRASTRUCTURE, see oracle/__init__.py).
 
   * ``gdl``        - Trainer.gradient_difference_loss, trainers/trainer.py:65-83
-  * ``bipatch_nce``- BiPatchNCE.forward, models/contrastive_loss.py:28-60 (forward value: the diag / non-diag
-                     split at :39-47 only changes gradients, the scores are gt_f . pred_f^T / temperature)
+  * ``bipatch_nce``- BiPatchNCE.forward, models/contrastive_loss.py:28-60, including the diag / non-diag split at
+                     :39-47 (the scores are gt_f . pred_f^T / temperature either way; the split stops the gradient
+                     of the direction-1 negatives, which matters for oracle/train.py)
   * ``criterion``  - Trainer.criterion, trainers/trainer.py:88-109
 Inputs are (P, B, E) sequence-first slices ``pred[-P:]`` / ``y_expected[-P:]`` like the reference's call sites
 (trainers/trainer.py:145, :224).  Pinned by tests/golden/losses.npz (oracle/make_golden_losses.py)."""
@@ -27,8 +28,9 @@ def bipatch_nce(x, y, temperature=0.07):
     hw = E // 4
     pred_f = x.permute(1, 0, 2).reshape(B * P, 4, hw).transpose(1, 2)   # (N T) (h w) C
     gt_f = y.permute(1, 0, 2).reshape(B * P, 4, hw).transpose(1, 2)
-    s1 = gt_f @ pred_f.transpose(1, 2) / temperature                     # contrastive_loss.py:39-42
-    s2 = pred_f @ gt_f.transpose(1, 2) / temperature                     # :45-48
+    eye = torch.eye(hw, dtype=x.dtype, device=x.device)
+    s1 = (gt_f @ pred_f.transpose(1, 2) * eye + gt_f @ pred_f.detach().transpose(1, 2) * (1.0 - eye)) / temperature   # :39-42
+    s2 = (pred_f @ gt_f.transpose(1, 2) * eye + pred_f @ gt_f.detach().transpose(1, 2) * (1.0 - eye)) / temperature   # :45-48
     diag = torch.arange(hw)
     l1 = (torch.logsumexp(s1, -1) - s1[:, diag, diag]).mean()            # CrossEntropyLoss vs identity target, :56
     l2 = (torch.logsumexp(s2, -1) - s2[:, diag, diag]).mean()            # :57

@@ -15,6 +15,8 @@ SYMBOLS = (
     "sdvg_version", "sdvg_last_error", "sdvg_create", "sdvg_destroy", "sdvg_workspace_bytes", "sdvg_set_weight",
     "sdvg_num_weights", "sdvg_weight_key", "sdvg_finalize_weights", "sdvg_forward", "sdvg_rollout",
     "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm", "sdvg_criterion",
+    "sdvg_train_backward", "sdvg_train_gradients", "sdvg_param_range", "sdvg_train_prediction", "sdvg_train_adam_step",
+    "sdvg_get_weight",
 )
 
 
@@ -23,6 +25,12 @@ class SdvgConfig(C.Structure):
                 ("num_decoder_layers", C.c_int32), ("latent_dim", C.c_int32), ("dim_feedforward", C.c_int32),
                 ("layer_norm_eps", C.c_float), ("max_clips", C.c_int32), ("max_tokens", C.c_int32),
                 ("max_history", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32)]
+
+
+class SdvgLossConfig(C.Structure):
+    _fields_ = [("frames_to_predict", C.c_int32), ("use_mse", C.c_int32), ("use_l1", C.c_int32), ("use_gdl", C.c_int32),
+                ("lambda_gdl", C.c_float), ("alpha", C.c_float), ("use_contrastive", C.c_int32),
+                ("temperature", C.c_float), ("lambda_contrastive", C.c_float)]
 
 
 _lib = None
@@ -66,6 +74,12 @@ def load(build_if_missing=True):
     lib.sdvg_launch_count.restype = C.c_int64
     lib.sdvg_gemm.argtypes = [i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(f32), vp]
     lib.sdvg_criterion.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, vp, vp]
+    lib.sdvg_train_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.POINTER(SdvgLossConfig), vp, vp, i32, vp]
+    lib.sdvg_train_gradients.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sdvg_param_range.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sdvg_train_prediction.argtypes = [vp, C.POINTER(vp)]
+    lib.sdvg_train_adam_step.argtypes = [vp, f32, f32, f32, f32, f32, vp]
+    lib.sdvg_get_weight.argtypes = [vp, C.c_char_p, vp, vp]
     _lib = lib
     return lib
 

@@ -5,14 +5,15 @@ from .dist import pe_index_for, rollout_sharded, shard_bounds
 from .positional_encoding import PositionalEncoding
 from .predict import (LATENT_SCALE, SOS_VALUE, HostRollout, predict, predict_diff, predict_future, rollout,
                       rollout_from_host)
-from .trainer import BiPatchNCE, criterion, gradient_difference_loss, loss_terms, validation_step
+from .trainer import (AdamTrainer, BiPatchNCE, allreduce_buckets, criterion, gradient_difference_loss, loss_terms,
+                      validation_step)
 from .transformer import Identity, Transformer, TransformerFuture
 
 __all__ = ["Transformer", "TransformerFuture", "Identity", "PositionalEncoding", "predict", "predict_diff",
            "predict_future", "rollout", "rollout_from_host", "HostRollout",
            "rollout_sharded", "shard_bounds", "pe_index_for", "CONFIGS", "latent_dim", "parse_config_args",
            "LATENT_SCALE", "SOS_VALUE", "gemm", "build_library", "criterion", "gradient_difference_loss", "BiPatchNCE",
-           "loss_terms", "validation_step"]
+           "loss_terms", "validation_step", "AdamTrainer", "allreduce_buckets"]
 
 
 def build_library(force=False, verbose=False):

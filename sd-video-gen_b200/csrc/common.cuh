@@ -48,6 +48,11 @@ struct Epilogue {
   const float2* ln_stats = nullptr;
   const float* ln_w = nullptr;
   const float* ln_b = nullptr;
+  // training (backward GEMMs): alpha_dev multiplies like alpha but is read from device memory (1 / loss scale);
+  // gate zeroes the value where gate[row][col] <= 0 (ReLU backward against the saved activation), before the residual
+  const float* alpha_dev = nullptr;
+  const float* gate = nullptr;
+  int ld_gate = 0;
 };
 
 __device__ __forceinline__ int epi_out_row(const Epilogue& e, int row) {
@@ -75,6 +80,8 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, float acc, int row
   float v = acc;
   if (e.bias) v += __ldg(e.bias + col);
   v *= e.alpha;
+  if (e.alpha_dev) v *= __ldg(e.alpha_dev);
+  if (e.gate && __ldg(e.gate + static_cast<size_t>(row) * e.ld_gate + col) <= 0.0f) v = 0.0f;
   if (pe_row >= 0) v += __ldg(e.pe + static_cast<size_t>(pe_row) * e.ld_pe + col);
   if (e.relu) v = fmaxf(v, 0.0f);
   if (e.residual) {

@@ -90,6 +90,9 @@ class Engine {
   std::vector<WeightSlot> slots;
   std::map<std::string, int> slot_of;
 
+  float* arena = nullptr;     // every fp32 parameter, in slot order
+  size_t arena_count = 0;
+
   Linear embedding, out_proj;
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
@@ -282,8 +285,15 @@ class Engine {
     add_slot("out.weight", {E, d}, true, sa);
     add_slot("out.bias", {E}, false, false);
 
+    // all fp32 parameters live in one arena (64-float aligned slots) so that the gradient vector, the Adam
+    // moments and the NCCL all-reduce of the training step are single flat arrays with the same offsets
+    arena_count = 0;
+    for (auto& s : slots) arena_count += static_cast<size_t>(round_up(static_cast<int>(s.count), 64));
+    if ((e = dalloc(&arena, arena_count)) != cudaSuccess) return fail_cuda(e, "weight alloc");
+    size_t arena_off = 0;
     for (auto& s : slots) {
-      if ((e = dalloc(&s.dev, s.count)) != cudaSuccess) return fail_cuda(e, "weight alloc");
+      s.dev = arena + arena_off;
+      arena_off += static_cast<size_t>(round_up(static_cast<int>(s.count), 64));
       if (s.is_matrix && tc()) {
         const int rows = static_cast<int>(s.shape[0]), cols = static_cast<int>(s.shape[1]);
         s.ld16 = round_up(cols, kTcBK);

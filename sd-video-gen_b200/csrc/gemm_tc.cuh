@@ -260,7 +260,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
           v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           int out_row = row;
           if constexpr (FANCY) {
-            v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
+            const float al = e.alpha_dev ? e.alpha * __ldg(e.alpha_dev) : e.alpha;
+            v.x *= al; v.y *= al; v.z *= al; v.w *= al;
+            if (e.gate) {
+              const float4 gt = __ldg(reinterpret_cast<const float4*>(e.gate + static_cast<size_t>(row) * e.ld_gate + col));
+              v.x = gt.x > 0.f ? v.x : 0.f; v.y = gt.y > 0.f ? v.y : 0.f; v.z = gt.z > 0.f ? v.z : 0.f; v.w = gt.w > 0.f ? v.w : 0.f;
+            }
             if (e.pe || e.row_map) {
               const int b = row / e.rows_per_clip, sidx = row - b * e.rows_per_clip;
               if (e.pe) {
@@ -303,7 +308,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
 
 // The embedding / output projections are the only GEMMs that scale, add positional rows or remap output rows.
 inline bool epilogue_is_fancy(const Epilogue& e) {
-  return e.alpha != 1.0f || e.pe != nullptr || e.row_map != 0 || e.res_clip_rows != 0;
+  return e.alpha != 1.0f || e.pe != nullptr || e.row_map != 0 || e.res_clip_rows != 0 || e.alpha_dev != nullptr ||
+         e.gate != nullptr;
 }
 
 template <int BN, bool SPLIT, bool FANCY>
@@ -497,6 +503,7 @@ inline bool epilogue_vec4_ok(const Epilogue& e, int N) {
   if (e.pe && (!al(e.pe, 16) || e.ld_pe % 4 != 0)) return false;
   if (e.residual && (!al(e.residual, 16) || e.ld_res % 4 != 0)) return false;
   if (e.ln_stats && (!al(e.ln_stats, 8) || !al(e.ln_w, 16) || !al(e.ln_b, 16))) return false;
+  if (e.gate && (!al(e.gate, 16) || e.ld_gate % 4 != 0)) return false;
   if (e.out32 && (!al(e.out32, 16) || e.ld32 % 4 != 0)) return false;
   if (e.out_hi && (!al(e.out_hi, 8) || e.ld16 % 4 != 0)) return false;
   if (e.out_lo && !al(e.out_lo, 8)) return false;

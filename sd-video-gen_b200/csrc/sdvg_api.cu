@@ -4,11 +4,14 @@
 
 #include "engine.cuh"
 #include "loss.cuh"
+#include "train_engine.cuh"
 
 using sdvg::Engine;
 
 struct sdvg_handle {
   Engine eng;
+  sdvg::Trainer* trainer = nullptr;   // created by the first training call
+  ~sdvg_handle() { delete trainer; }
 };
 
 static thread_local std::string g_create_error;
@@ -65,6 +68,7 @@ int sdvg_set_weight(sdvg_handle* h, const char* key, const void* data, const int
   if (!h) return SDVG_ERR_INVALID;
   if (!data || !shape) return h->eng.fail(SDVG_ERR_INVALID, "null argument");
   cudaSetDevice(h->eng.cfg.device);
+  if (h->trainer) h->trainer->wt_stale = true;
   return h->eng.set_weight(key, data, shape, ndim);
 }
 
@@ -110,6 +114,81 @@ int sdvg_timing_read(sdvg_handle* h, double* ms, int64_t* launches, double* flop
 }
 
 int64_t sdvg_launch_count(const sdvg_handle* h) { return h ? h->eng.launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// training step
+static sdvg::Trainer* trainer_of(sdvg_handle* h) {
+  if (!h->trainer) h->trainer = new (std::nothrow) sdvg::Trainer(h->eng);
+  return h->trainer;
+}
+
+int sdvg_train_backward(sdvg_handle* h, const float* src, const float* tgt, const float* expected, int32_t B, int32_t S_src,
+                        int32_t S_tgt, const sdvg_loss_config* loss, const int32_t* pe_index, float* losses, int32_t part,
+                        void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  if (!loss) return h->eng.fail(SDVG_ERR_INVALID, "null loss configuration");
+  cudaSetDevice(h->eng.cfg.device);
+  sdvg::Trainer* t = trainer_of(h);
+  if (!t) return h->eng.fail(SDVG_ERR_INVALID, "out of host memory");
+  sdvg::TrainLoss lc{loss->frames_to_predict, loss->use_mse != 0, loss->use_l1 != 0, loss->use_gdl != 0, loss->lambda_gdl, loss->alpha,
+                     loss->use_contrastive != 0, loss->temperature, loss->lambda_contrastive};
+  try {
+    return t->forward_backward(src, tgt, expected, B, S_src, S_tgt, lc, pe_index, losses, part, static_cast<cudaStream_t>(stream));
+  } catch (const std::exception& ex) {
+    return h->eng.fail(SDVG_ERR_INVALID, "exception: %s", ex.what());
+  }
+}
+
+int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t* decoder_offset) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  sdvg::Trainer* t = trainer_of(h);
+  if (!t) return h->eng.fail(SDVG_ERR_INVALID, "out of host memory");
+  int rc = t->init();
+  if (rc != SDVG_OK) return rc;
+  if (grads) *grads = t->grads;
+  if (count) *count = static_cast<int64_t>(h->eng.arena_count);
+  if (decoder_offset) *decoder_offset = static_cast<int64_t>(t->decoder_offset);
+  return SDVG_OK;
+}
+
+int sdvg_param_range(const sdvg_handle* h, const char* key, int64_t* offset, int64_t* count) {
+  if (!h) return SDVG_ERR_INVALID;
+  auto it = h->eng.slot_of.find(key ? key : "");
+  if (it == h->eng.slot_of.end()) return SDVG_ERR_INVALID;
+  const sdvg::WeightSlot& s = h->eng.slots[it->second];
+  if (offset) *offset = static_cast<int64_t>(s.dev - h->eng.arena);
+  if (count) *count = static_cast<int64_t>(s.count);
+  return SDVG_OK;
+}
+
+int sdvg_train_prediction(sdvg_handle* h, const float** pred) {
+  if (!h || !pred) return SDVG_ERR_INVALID;
+  if (!h->trainer || !h->trainer->ready || h->trainer->Bc == 0) return h->eng.fail(SDVG_ERR_STATE, "no training forward pass has run");
+  *pred = h->trainer->pred;
+  return SDVG_OK;
+}
+
+int sdvg_train_adam_step(sdvg_handle* h, float lr, float beta1, float beta2, float eps, float grad_mul, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  if (!h->trainer) return h->eng.fail(SDVG_ERR_STATE, "no gradients: call sdvg_train_backward first");
+  return h->trainer->adam_step(lr, beta1, beta2, eps, grad_mul, static_cast<cudaStream_t>(stream));
+}
+
+int sdvg_get_weight(sdvg_handle* h, const char* key, float* out, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  if (!out) return h->eng.fail(SDVG_ERR_INVALID, "null argument");
+  auto it = h->eng.slot_of.find(key ? key : "");
+  if (it == h->eng.slot_of.end()) return h->eng.fail(SDVG_ERR_INVALID, "unknown state_dict key '%s'", key ? key : "(null)");
+  cudaSetDevice(h->eng.cfg.device);
+  const sdvg::WeightSlot& s = h->eng.slots[it->second];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(out, s.dev, s.count * sizeof(float), cudaMemcpyDefault, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->eng.fail_cuda(e, "weight read-back");
+  return SDVG_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W, const float* bias, int32_t relu,

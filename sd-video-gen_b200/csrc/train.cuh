@@ -1,0 +1,420 @@
+// Kernels of the training step (trainers/trainer.py:123-165: teacher-forced forward, criterion, loss.backward(),
+// Adam) that are not GEMMs.  Every linear layer's backward is two tensor-core GEMMs of the same kernels the
+// forward uses (gemm_tc*.cuh):
+//     dX[M,K] = dY[M,N] . W[N,K]          A = dY planes,            B = W^T planes [K][N]
+//     dW[N,K] = dY^T[N,M] . X[M,K]        A = dY^T planes [N][Mp],  B = X^T planes [K][Mp]
+// so what is needed around them is (1) pack_t: fp32 matrix -> operand planes, transposed operand planes and
+// column sums (the bias gradient) in one pass, (2) LayerNorm backward, (3) attention backward, (4) the gradient of
+// the criterion (MSE / L1 / GDL / BiPatchNCE), (5) Adam.  All HBM/L2-bound streaming kernels with coalesced
+// 128-byte rows; nothing here allocates or synchronises.
+//
+// Gradients flow through 16-bit operand planes, so they are kept multiplied by a power-of-two loss scale S chosen
+// on the device from max|dL/dpred| (loss_scale_kernel); every parameter gradient is multiplied by 1/S where it is
+// written (GEMM epilogue Epilogue::alpha_dev, column sums here), so the gradient vector handed to the all-reduce
+// and to Adam is unscaled fp32.
+#pragma once
+#include "common.cuh"
+
+namespace sdvg {
+
+constexpr int kTrainMaxS = 16;   // tokens per clip in a training step (the reference uses 6 and 5)
+
+// ------------------------------------------------------------------------------------------------ pack_t
+struct PackTArgs {
+  const float* src; int ld_src;        // [R][C] fp32
+  int R, C;
+  int perm_S, perm_B;                  // perm_S > 0: destination row r reads source row (r % S) * B + r / S (sequence-major -> clip-major)
+  float mul; const float* mul_dev;     // v = src * mul * (mul_dev ? *mul_dev : 1)
+  uint16_t* out_hi; uint16_t* out_lo; int ld16;            // planes [R][C] (nullable)
+  uint16_t* t_hi; uint16_t* t_lo; int ld_t; int Rpad;      // transposed planes [C][ld_t]; columns [R, Rpad) are zero-filled (nullable)
+  float* colsum; const float* colsum_mul_dev; int colsum_accumulate;   // colsum[c] (+)= (*colsum_mul_dev) * sum_r v[r][c]  (nullable)
+  int bf16;
+  int rows_per_block;                  // rows one CTA walks through (a multiple of 128)
+};
+
+__global__ void __launch_bounds__(256) pack_t_kernel(const __grid_constant__ PackTArgs a) {
+  __shared__ float tile[32][129];
+  __shared__ float red[8][32];
+  pdl_wait();
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  const float mul = a.mul * (a.mul_dev ? __ldg(a.mul_dev) : 1.0f);
+  const int row_begin = blockIdx.y * a.rows_per_block;
+  int row_end = row_begin + a.rows_per_block;
+  const int limit = a.t_hi ? a.Rpad : a.R;
+  if (row_end > limit) row_end = limit;
+  float cs = 0.f;
+  for (int r0 = row_begin; r0 < row_end; r0 += 128) {
+#pragma unroll 4
+    for (int rl = warp; rl < 128; rl += 8) {
+      const int r = r0 + rl;
+      float v = 0.f;
+      if (r < a.R && c < a.C) {
+        const int sr = a.perm_S > 0 ? (r % a.perm_S) * a.perm_B + r / a.perm_S : r;
+        v = __ldg(a.src + static_cast<size_t>(sr) * a.ld_src + c) * mul;
+        if (a.out_hi) {
+          const uint16_t h = to_plane_hi(v, a.bf16);
+          a.out_hi[static_cast<size_t>(r) * a.ld16 + c] = h;
+          if (a.out_lo) a.out_lo[static_cast<size_t>(r) * a.ld16 + c] = to_plane_lo(v, h);
+        }
+      }
+      cs += v;
+      tile[lane][rl] = v;
+    }
+    __syncthreads();
+    if (a.t_hi) {
+      // warp w writes columns c0 + w, w + 8, ...; each lane 4 consecutive rows (8 bytes per plane)
+      for (int cl = warp; cl < 32; cl += 8) {
+        const int cc = blockIdx.x * 32 + cl;
+        const int r = r0 + lane * 4;
+        if (cc < a.C && r < a.Rpad) {
+          uint16_t h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float v = tile[cl][lane * 4 + i];
+            h[i] = to_plane_hi(v, a.bf16);
+            l[i] = to_plane_lo(v, h[i]);
+          }
+          const size_t o = static_cast<size_t>(cc) * a.ld_t + r;
+          *reinterpret_cast<uint2*>(a.t_hi + o) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+          if (a.t_lo) *reinterpret_cast<uint2*>(a.t_lo + o) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (a.colsum) {
+    red[warp][lane] = cs;
+    __syncthreads();
+    if (warp == 0 && c < a.C) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][lane];
+      t *= a.colsum_mul_dev ? __ldg(a.colsum_mul_dev) : 1.0f;
+      a.colsum[c] = a.colsum_accumulate ? a.colsum[c] + t : t;
+    }
+  }
+}
+
+inline cudaError_t launch_pack_t(PackTArgs a, cudaStream_t stream) {
+  if (a.t_hi && (a.Rpad % 4 != 0 || a.ld_t % 4 != 0)) return cudaErrorInvalidValue;
+  const int limit = a.t_hi ? a.Rpad : a.R;
+  // the column sums need every row in one CTA; otherwise split long matrices (weights) over the grid
+  a.rows_per_block = a.colsum ? ((limit + 127) / 128) * 128 : 512;
+  const dim3 grid(ceil_div(a.C, 32), ceil_div(limit, a.rows_per_block));
+  return launch_kernel(pack_t_kernel, grid, dim3(256), 0, stream, a);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// y = LN(x) = xhat * w + b, xhat = (x - mean) * rstd.  With g = dy * w:
+//   dx = rstd * (g - mean_j(g) - xhat * mean_j(g * xhat));   dw = sum_rows dy * xhat;   db = sum_rows dy.
+// CTAs [0, rows): one row each (dx).  CTAs [rows, rows + d/32): 32 columns each over all rows (dw, db).
+struct LnBwdArgs {
+  const float* dy; int ld_dy;
+  const float* x; int ld_x;        // saved LayerNorm input
+  const float2* stats;             // (mean, rstd) per row, saved by the forward kernel
+  const float* w;
+  int rows, d;
+  float* dx; int ld_dx;
+  float* dw; float* db;            // parameter gradients [d]
+  const float* param_mul_dev;      // 1 / loss scale
+};
+
+__global__ void __launch_bounds__(256) ln_backward_kernel(const __grid_constant__ LnBwdArgs a) {
+  __shared__ float red[2][8][32];
+  pdl_wait();
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (static_cast<int>(blockIdx.x) < a.rows) {
+    const int r = blockIdx.x;
+    const float2 st = __ldg(a.stats + r);
+    const float* dy = a.dy + static_cast<size_t>(r) * a.ld_dy;
+    const float* x = a.x + static_cast<size_t>(r) * a.ld_x;
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = threadIdx.x; j < a.d; j += 256) {
+      const float g = __ldg(dy + j) * __ldg(a.w + j);
+      const float xh = (__ldg(x + j) - st.x) * st.y;
+      s1 += g; s2 = fmaf(g, xh, s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) { red[0][warp][0] = s1; red[1][warp][0] = s2; }
+    __syncthreads();
+    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s1 += red[0][w][0]; s2 += red[1][w][0]; }
+    const float m1 = s1 / static_cast<float>(a.d), m2 = s2 / static_cast<float>(a.d);
+    float* dx = a.dx + static_cast<size_t>(r) * a.ld_dx;
+    for (int j = threadIdx.x; j < a.d; j += 256) {
+      const float g = __ldg(dy + j) * __ldg(a.w + j);
+      const float xh = (__ldg(x + j) - st.x) * st.y;
+      dx[j] = st.y * (g - m1 - xh * m2);
+    }
+    return;
+  }
+  const int c = (blockIdx.x - a.rows) * 32 + lane;
+  float sw = 0.f, sb = 0.f;
+  if (c < a.d) {
+    for (int r = warp; r < a.rows; r += 8) {
+      const float2 st = __ldg(a.stats + r);
+      const float g = __ldg(a.dy + static_cast<size_t>(r) * a.ld_dy + c);
+      const float xh = (__ldg(a.x + static_cast<size_t>(r) * a.ld_x + c) - st.x) * st.y;
+      sw = fmaf(g, xh, sw); sb += g;
+    }
+  }
+  red[0][warp][lane] = sw; red[1][warp][lane] = sb;
+  __syncthreads();
+  if (warp == 0 && c < a.d) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tw += red[0][w][lane]; tb += red[1][w][lane]; }
+    const float m = a.param_mul_dev ? __ldg(a.param_mul_dev) : 1.0f;
+    a.dw[c] = tw * m; a.db[c] = tb * m;
+  }
+}
+
+inline cudaError_t launch_ln_backward(const LnBwdArgs& a, cudaStream_t stream) {
+  return launch_kernel(ln_backward_kernel, dim3(a.rows + ceil_div(a.d, 32)), dim3(256), 0, stream, a);
+}
+
+// ------------------------------------------------------------------------------------------------ attention backward
+// One warp per (clip, head); S <= kTrainMaxS so the score matrices live in shared memory (1 KB each per warp).
+//   P = softmax(scale Q K^T + mask);  O = P V
+//   dV = P^T dO;  dP = dO V^T;  dS = P o (dP - rowsum(P o dP));  dQ = scale dS K;  dK = scale dS^T Q
+struct AttnBwdArgs {
+  const float* q; int ldq; const float* k; const float* v; int ldkv;
+  const float* dO; int ld_do;
+  float* dq; int ld_dq; float* dk; float* dv; int ld_dkv;
+  int clips, heads, hd, Sq, Sk, causal;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_constant__ AttnBwdArgs a) {
+  __shared__ float sP[4][kTrainMaxS][kTrainMaxS];
+  __shared__ float sD[4][kTrainMaxS][kTrainMaxS];
+  pdl_wait();
+  pdl_trigger();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + wib;
+  if (wg >= a.clips * a.heads) return;
+  const int b = wg / a.heads, h = wg - b * a.heads;
+  const int hd = a.hd, Sq = a.Sq, Sk = a.Sk;
+  const float* q = a.q + static_cast<size_t>(b) * Sq * a.ldq + h * hd;
+  const float* k = a.k + static_cast<size_t>(b) * Sk * a.ldkv + h * hd;
+  const float* v = a.v + static_cast<size_t>(b) * Sk * a.ldkv + h * hd;
+  const float* dO = a.dO + static_cast<size_t>(b) * Sq * a.ld_do + h * hd;
+  float (*P)[kTrainMaxS] = sP[wib];
+  float (*D)[kTrainMaxS] = sD[wib];
+  for (int i = 0; i < Sq; ++i) {
+    for (int j = 0; j < Sk; ++j) {
+      float s = 0.f, dp = 0.f;
+      for (int e = lane; e < hd; e += 32) {
+        s = fmaf(__ldg(q + static_cast<size_t>(i) * a.ldq + e), __ldg(k + static_cast<size_t>(j) * a.ldkv + e), s);
+        dp = fmaf(__ldg(dO + static_cast<size_t>(i) * a.ld_do + e), __ldg(v + static_cast<size_t>(j) * a.ldkv + e), dp);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
+      if (lane == 0) {
+        const bool masked = a.causal && j > i + (Sk - Sq);
+        P[i][j] = masked ? -INFINITY : s * a.scale;
+        D[i][j] = dp;
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < Sq) {
+    const int i = lane;
+    float mx = -INFINITY;
+    for (int j = 0; j < Sk; ++j) mx = fmaxf(mx, P[i][j]);
+    float sum = 0.f;
+    for (int j = 0; j < Sk; ++j) { const float p = __expf(P[i][j] - mx); P[i][j] = p; sum += p; }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+    for (int j = 0; j < Sk; ++j) { P[i][j] *= inv; dot = fmaf(P[i][j], D[i][j], dot); }
+    for (int j = 0; j < Sk; ++j) D[i][j] = P[i][j] * (D[i][j] - dot);   // dS
+  }
+  __syncwarp();
+  for (int e = lane; e < hd; e += 32) {
+    for (int i = 0; i < Sq; ++i) {
+      float acc = 0.f;
+      for (int j = 0; j < Sk; ++j) acc = fmaf(D[i][j], __ldg(k + static_cast<size_t>(j) * a.ldkv + e), acc);
+      a.dq[(static_cast<size_t>(b) * Sq + i) * a.ld_dq + h * hd + e] = acc * a.scale;
+    }
+    for (int j = 0; j < Sk; ++j) {
+      float ak = 0.f, av = 0.f;
+      for (int i = 0; i < Sq; ++i) {
+        ak = fmaf(D[i][j], __ldg(q + static_cast<size_t>(i) * a.ldq + e), ak);
+        av = fmaf(P[i][j], __ldg(dO + static_cast<size_t>(i) * a.ld_do + e), av);
+      }
+      a.dk[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = ak * a.scale;
+      a.dv[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = av;
+    }
+  }
+}
+
+inline cudaError_t launch_attention_backward(const AttnBwdArgs& a, cudaStream_t stream) {
+  if (a.Sq > kTrainMaxS || a.Sk > kTrainMaxS) return cudaErrorInvalidValue;
+  return launch_kernel(attention_backward_kernel, dim3(ceil_div(a.clips * a.heads, 4)), dim3(128), 0, stream, a);
+}
+
+// ------------------------------------------------------------------------------------------------ criterion gradient
+// d criterion / d pred for the (P, B, E) slices of trainers/trainer.py:145 (sequence-major, E = 4 h w):
+//   MSE 2 (x - y) / n;  L1 sign(x - y) / n;  GDL (trainers/trainer.py:65-83): each forward difference a = x[+1] - x
+//   contributes alpha |abs(a) - abs(b)|^(alpha-1) sign(abs(a) - abs(b)) sign(a) / n to x[+1] and its negative to x;
+//   BiPatchNCE (models/contrastive_loss.py:28-60): direction 1 back-propagates through the diagonal scores only
+//   (the off-diagonal ones use pred.detach()), direction 2 through the whole row.
+struct LossGradArgs {
+  const float* x; const float* y;   // prediction, ground truth (P, B, E)
+  int P, B, h, w;
+  float c_mse, c_l1, c_gdl, alpha;  // coefficients already divided by n = P B E
+  float c_nce, inv_temperature;     // 0.5 * lambda_c / (P B hw)
+  float* grad;                      // (P, B, E), overwritten by the elementwise kernel, += by the NCE kernel
+  unsigned int* amax_bits;          // max |grad| as float bits (atomicMax on non-negative floats)
+};
+
+__device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+__device__ __forceinline__ float gdl_dterm(float da, float db, float alpha) {
+  const float u = fabsf(da) - fabsf(db);
+  float m;
+  if (alpha == 2.0f) m = 2.0f * fabsf(u);
+  else if (alpha == 1.0f) m = 1.0f;
+  else m = alpha * powf(fabsf(u), alpha - 1.0f);
+  return m * sgn(u) * sgn(da);
+}
+
+__global__ void __launch_bounds__(256) loss_grad_elementwise_kernel(const __grid_constant__ LossGradArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const int hw = a.h * a.w, E = 4 * hw;
+  const long long total = static_cast<long long>(a.P) * a.B * E;
+  float amax = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const float xv = __ldg(a.x + i), yv = __ldg(a.y + i);
+    const float d = xv - yv;
+    float g = a.c_mse * 2.0f * d + a.c_l1 * sgn(d);
+    if (a.c_gdl != 0.f) {
+      const int e = static_cast<int>(i % E);
+      const int p = e % hw, r = p / a.w, c = p - r * a.w;
+      float t = 0.f;
+      if (r + 1 < a.h) t -= gdl_dterm(__ldg(a.x + i + a.w) - xv, __ldg(a.y + i + a.w) - yv, a.alpha);
+      if (r > 0) t += gdl_dterm(xv - __ldg(a.x + i - a.w), yv - __ldg(a.y + i - a.w), a.alpha);
+      if (c + 1 < a.w) t -= gdl_dterm(__ldg(a.x + i + 1) - xv, __ldg(a.y + i + 1) - yv, a.alpha);
+      if (c > 0) t += gdl_dterm(xv - __ldg(a.x + i - 1), yv - __ldg(a.y + i - 1), a.alpha);
+      g = fmaf(a.c_gdl, t, g);
+    }
+    a.grad[i] = g;
+    amax = fmaxf(amax, fabsf(g));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(a.amax_bits, __float_as_uint(amax));
+}
+
+// One CTA per (clip n, frame t), one thread per patch i (strided).  Feature (i, c) = v[t][n][c*hw + i].
+__global__ void __launch_bounds__(256) loss_grad_nce_kernel(const __grid_constant__ LossGradArgs a) {
+  extern __shared__ float4 nce_g_smem[];   // [2][hw]: pred, gt
+  pdl_wait();
+  pdl_trigger();
+  const int hw = a.h * a.w;
+  const int n = blockIdx.x % a.B, t = blockIdx.x / a.B;
+  const size_t base = (static_cast<size_t>(t) * a.B + n) * 4 * hw;
+  float4* sp = nce_g_smem;
+  float4* sg = nce_g_smem + hw;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    sp[i] = make_float4(__ldg(a.x + base + i), __ldg(a.x + base + hw + i), __ldg(a.x + base + 2 * hw + i), __ldg(a.x + base + 3 * hw + i));
+    sg[i] = make_float4(__ldg(a.y + base + i), __ldg(a.y + base + hw + i), __ldg(a.y + base + 2 * hw + i), __ldg(a.y + base + 3 * hw + i));
+  }
+  __syncthreads();
+  const float it = a.inv_temperature;
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const float4 pi = sp[i], gi = sg[i];
+    // direction 1, row i: scores gt_i . pred_j / tau; only p1[i][i] is needed
+    float m1 = -INFINITY, l1 = 0.f;
+    // direction 2, row i: scores pred_i . gt_j / tau; softmax-weighted sum of gt_j (online rescaling)
+    float m2 = -INFINITY, l2 = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < hw; ++j) {
+      const float4 pj = sp[j], gj = sg[j];
+      const float s1 = (gi.x * pj.x + gi.y * pj.y + gi.z * pj.z + gi.w * pj.w) * it;
+      const float s2 = (pi.x * gj.x + pi.y * gj.y + pi.z * gj.z + pi.w * gj.w) * it;
+      if (s1 > m1) { l1 *= __expf(m1 - s1); m1 = s1; }
+      l1 += __expf(s1 - m1);
+      if (s2 > m2) {
+        const float f = __expf(m2 - s2);
+        l2 *= f; acc.x *= f; acc.y *= f; acc.z *= f; acc.w *= f; m2 = s2;
+      }
+      const float e2 = __expf(s2 - m2);
+      l2 += e2;
+      acc.x = fmaf(e2, gj.x, acc.x); acc.y = fmaf(e2, gj.y, acc.y); acc.z = fmaf(e2, gj.z, acc.z); acc.w = fmaf(e2, gj.w, acc.w);
+    }
+    const float sii = (gi.x * pi.x + gi.y * pi.y + gi.z * pi.z + gi.w * pi.w) * it;
+    const float p1 = __expf(sii - m1) / l1;
+    const float inv2 = 1.0f / l2;
+    const float k = a.c_nce * it;
+    const float g0 = k * ((p1 - 2.0f) * gi.x + acc.x * inv2);
+    const float g1 = k * ((p1 - 2.0f) * gi.y + acc.y * inv2);
+    const float g2 = k * ((p1 - 2.0f) * gi.z + acc.z * inv2);
+    const float g3 = k * ((p1 - 2.0f) * gi.w + acc.w * inv2);
+    float* o = a.grad + base + i;
+    const float r0 = o[0] + g0, r1 = o[hw] + g1, r2 = o[2 * hw] + g2, r3 = o[3 * hw] + g3;
+    o[0] = r0; o[hw] = r1; o[2 * hw] = r2; o[3 * hw] = r3;
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(r0), fabsf(r1))), fmaxf(fabsf(r2), fabsf(r3)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(a.amax_bits, __float_as_uint(amax));
+}
+
+// scale[0] = S = 2^k with S * amax in [32, 64), scale[1] = 1 / S; resets amax for the next step.
+__global__ void loss_scale_kernel(unsigned int* amax_bits, float* scale) {
+  pdl_wait();
+  pdl_trigger();
+  const float amax = __uint_as_float(*amax_bits);
+  float s = 1.0f;
+  if (amax > 0.f && amax < INFINITY) {
+    int ex;
+    frexpf(amax, &ex);            // amax = f * 2^ex, f in [0.5, 1)
+    int k = 6 - ex;
+    k = k > 100 ? 100 : (k < -100 ? -100 : k);
+    s = ldexpf(1.0f, k);
+  }
+  scale[0] = s; scale[1] = 1.0f / s;
+  *amax_bits = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam(params, lr) as constructed at trainers/trainer.py:365: betas (0.9, 0.999), eps 1e-8, no weight
+// decay, no amsgrad.  One flat pass over all parameters: 16 bytes read, 12 written per parameter.
+struct AdamArgs {
+  float* p; const float* g; float* m; float* v;
+  long long n;
+  float beta1, beta2, eps, step_size, inv_bc2_sqrt, gmul;   // step_size = lr / (1 - beta1^t); gmul = 1 / world size
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const long long n4 = a.n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    float4 p = reinterpret_cast<float4*>(a.p)[i];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g) + i);
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    float* pp = &p.x; const float* gp = &g4.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float g = gp[k] * a.gmul;
+      mp[k] = mp[k] + (g - mp[k]) * (1.0f - a.beta1);
+      vp[k] = vp[k] * a.beta2 + (1.0f - a.beta2) * g * g;
+      const float denom = sqrtf(vp[k]) * a.inv_bc2_sqrt + a.eps;
+      pp[k] = pp[k] - a.step_size * (mp[k] / denom);
+    }
+    reinterpret_cast<float4*>(a.p)[i] = p;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+  }
+}
+
+}  // namespace sdvg

@@ -6,8 +6,11 @@ validation loop (trainers/trainer.py:192-260) and for logging in the training lo
   * ``BiPatchNCE``                     - models/contrastive_loss.py:9-60 (same constructor; no (N*T, hw, hw) mask buffer)
   * ``validation_step(model, batch)``  - the body of validation_loop for one batch of latents (:203-224)
 
-All of them run hand-written CUDA through ``sdvg_criterion`` (include/sdvg.h); CPU tensors raise.  The backward
-pass / optimiser step of the training loop are not part of this build."""
+  * ``AdamTrainer``                    - opt = Adam(model.parameters(), lr) (:365) + the body of train_loop (:123-162):
+                                         teacher-forced forward, criterion, backward, Adam step, and - one process per
+                                         GPU - the NCCL all-reduce of the flat gradient vector in two buckets
+
+All of them run hand-written CUDA through ``sdvg_criterion`` / ``sdvg_train_*`` (include/sdvg.h); CPU tensors raise."""
 import ctypes as C
 import math
 
@@ -92,3 +95,143 @@ def validation_step(model, new_batch, frames_to_predict, loss_fn):
         pred = model(new_batch, y_input.contiguous(), "causal")
         loss = loss_fn(pred[-frames_to_predict:], y_expected[-frames_to_predict:].contiguous())
     return loss, pred
+
+
+class _DeviceArray:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+def allreduce_buckets(flat, split, world_size, group=None, streams=None):
+    """Sum-all-reduce ``flat[split:]`` then ``flat[:split]`` (the order the backward pass finishes them in).  Works on
+    any backend (NCCL on the GPU; gloo on CPU tensors in the host-logic tests).  Returns the async work handles."""
+    import torch.distributed as dist
+    works = []
+    for lo, hi in ((split, flat.numel()), (0, split)):
+        if hi > lo:
+            works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return works
+
+
+class AdamTrainer:
+    """``opt = optim.Adam(model.parameters(), lr=lr)`` (trainers/trainer.py:365) bound to the loss configuration of
+    ``Trainer.criterion`` (:88) - ``step(new_batch)`` is one iteration of ``train_loop`` (:123-162).
+
+    Data parallel (one process per GPU, ``torch.distributed`` initialised with NCCL): every rank passes its own shard
+    of the global batch and ``pe_index`` = the clips' positions in the global batch; gradients are summed over ranks
+    in two buckets - the decoder-side bucket is reduced while the encoder backward still runs - and Adam applies
+    their mean on every rank, so all replicas stay identical.  Dropout is the identity (see include/sdvg.h)."""
+
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, *, frames_to_predict=5, use_mse=True, use_L1=False,
+                 use_gdl=True, lambda_gdl=1, alpha=2, use_contrastive=True, temperature=0.07, lambda_contrastive=0.1,
+                 overlap=True, ignore_dropout=False):
+        if use_mse and use_L1:
+            raise RuntimeError("Invalid loss function combination")        # trainers/trainer.py:107-109
+        if getattr(model, "dropout_p", 0.0) > 0 and not ignore_dropout:
+            raise RuntimeError("the training step treats dropout as the identity (torch's dropout RNG stream cannot be "
+                               "reproduced); build the model with dropout_p=0 or pass ignore_dropout=True")
+        self.model, self.lr, self.betas, self.eps = model, float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.loss_cfg = _lib.SdvgLossConfig(int(frames_to_predict), int(bool(use_mse)), int(bool(use_L1)), int(bool(use_gdl)),
+                                            float(lambda_gdl), float(alpha), int(bool(use_contrastive)), float(temperature),
+                                            float(lambda_contrastive))
+        self.overlap = overlap
+        self._comm_stream = None
+        self.steps = 0
+
+    # -- views of library-owned memory
+    def _handle(self, device):
+        return self.model.engine(device)
+
+    def gradients(self, device=None):
+        """(flat fp32 gradient tensor [view], offset of the decoder-side bucket)."""
+        device = device or next(self.model.parameters()).device
+        h = self._handle(device)
+        ptr, n, off = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().sdvg_train_gradients(h, C.byref(ptr), C.byref(n), C.byref(off)), h)
+        return torch.as_tensor(_DeviceArray(ptr.value, n.value), device=device), int(off.value)
+
+    def gradient(self, key, device=None):
+        """Gradient of one state_dict entry, shaped like the parameter (a view)."""
+        device = device or next(self.model.parameters()).device
+        flat, _ = self.gradients(device)
+        off, cnt = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().sdvg_param_range(self._handle(device), key.encode(), C.byref(off), C.byref(cnt)))
+        return flat[off.value: off.value + cnt.value].view(self.model.state_dict()[key].shape)
+
+    def prediction(self, B, S_tgt, device=None):
+        device = device or next(self.model.parameters()).device
+        h = self._handle(device)
+        ptr = C.c_void_p()
+        _lib.check(_lib.load().sdvg_train_prediction(h, C.byref(ptr)), h)
+        E = self.model.latent_dim
+        return torch.as_tensor(_DeviceArray(ptr.value, S_tgt * B * E), device=device).view(S_tgt, B, E)
+
+    def step(self, new_batch, pe_index=None):
+        """One training iteration on latents ``new_batch`` (B, T+1, E) incl. the SOS frame (trainers/trainer.py:123-162).
+        Returns the device tensor [total, mse, l1, gdl, contrastive] of this rank's shard."""
+        import torch.distributed as dist
+        if not new_batch.is_cuda:
+            raise RuntimeError("sdvg_b200 training runs on CUDA only (no CPU fallback)")
+        device = new_batch.device
+        new_batch = new_batch.detach().float().contiguous()
+        B, S, E = new_batch.shape
+        y_input = new_batch[:, :-1].contiguous()                                   # :126
+        y_expected = new_batch[:, 1:].permute(1, 0, 2).contiguous()                # :129-132
+        self.model.reserve(max_clips=B, max_tokens=S)
+        h = self._handle(device)
+        lib = _lib.load()
+        pe_ptr = None
+        if pe_index is not None:
+            pe_index = pe_index.to(device=device, dtype=torch.int32).contiguous()
+            pe_ptr = pe_index.data_ptr()
+        losses = torch.empty(5, device=device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(device)
+        sp = C.c_void_p(stream.cuda_stream)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+        def backward(part):
+            _lib.check(lib.sdvg_train_backward(h, new_batch.data_ptr(), y_input.data_ptr(), y_expected.data_ptr(), B, S, S - 1,
+                                               C.byref(self.loss_cfg), pe_ptr, losses.data_ptr(), part, sp), h)
+
+        if world == 1:
+            backward(0)
+        else:
+            flat, split = self.gradients(device)
+            if self.overlap:
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(device)
+                backward(1)
+                self._comm_stream.wait_stream(stream)
+                with torch.cuda.stream(self._comm_stream):
+                    w1 = dist.all_reduce(flat[split:], op=dist.ReduceOp.SUM, async_op=True)
+                backward(2)
+                w1.wait()                                  # orders the current stream after the first bucket's reduction
+                stream.wait_stream(self._comm_stream)
+                dist.all_reduce(flat[:split], op=dist.ReduceOp.SUM)
+            else:
+                backward(0)
+                for w in allreduce_buckets(flat, split, world):
+                    w.wait()
+        _lib.check(lib.sdvg_train_adam_step(h, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / world, sp), h)
+        self.steps += 1
+        self._dirty = True
+        return losses
+
+    def pull_weights(self):
+        """Copy the trained parameters back into the module (``model.state_dict()`` for torch.save, :294)."""
+        device = next(self.model.parameters()).device
+        h = self._handle(device)
+        lib = _lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        with torch.no_grad():
+            for k, p in self.model.named_parameters():
+                if k == "learned_tgt":
+                    continue
+                buf = torch.empty_like(p, dtype=torch.float32).contiguous()
+                _lib.check(lib.sdvg_get_weight(h, k.encode(), C.c_void_p(buf.data_ptr()), stream), h)
+                p.copy_(buf)
+        self.model._weights_stamp = self.model._stamp()     # the engine already holds exactly these values
+        return self.model

@@ -1,0 +1,162 @@
+"""GPU: the training step (trainers/trainer.py:123-162 - teacher-forced forward, criterion, backward, Adam) through
+libsdvg's C ABI against (a) golden values of the unmodified reference under torch autograd
+(tests/golden/train_step.npz, oracle/make_golden_train.py) and (b) the oracle on the same seeded inputs.
+
+Tolerance: fp32 mode (split-precision tensor-core GEMMs), per parameter tensor max|ours - ref| <= 1e-4 * max|ref|
+for gradients; losses to 1e-5 relative; weights after two Adam steps to 2e-3 of the total parameter change."""
+import numpy as np
+import pytest
+import torch
+
+import sdvg_b200
+from conftest import load_golden, sd_checksum
+from oracle import train as OT
+from oracle.ref_module import RefTransformer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOLG = 1e-4
+
+
+def sample(t, n=64):
+    f = t.detach().reshape(-1)
+    idx = torch.linspace(0, f.numel() - 1, min(n, f.numel())).long().to(f.device)
+    return f[idx]
+
+
+def build_pair(d, H, Le, Ld, seed, frame_size=64, precision="fp32"):
+    torch.manual_seed(seed)
+    ref = RefTransformer(0, d, H, Le, Ld, 0.0, frame_size=frame_size)
+    m = sdvg_b200.Transformer(0, d, H, Le, Ld, 0.0, frame_size=frame_size, precision=precision)
+    m.load_state_dict(ref.state_dict())
+    return m.to(DEV), ref
+
+
+CASES = {
+    "c5": dict(use_mse=True, use_L1=False, use_gdl=True, lambda_gdl=1, alpha=2, use_contrastive=True, temperature=0.07,
+               lambda_contrastive=0.1),
+    "l1": dict(use_mse=False, use_L1=True, use_gdl=False, use_contrastive=False),
+    "gdl1": dict(use_mse=False, use_L1=True, use_gdl=True, lambda_gdl=0.5, alpha=1, use_contrastive=True, temperature=0.1,
+                 lambda_contrastive=0.05),
+}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_train_step_matches_reference_golden(tag):
+    g = load_golden("train_step")
+    d, H, Le, Ld, E = (int(v) for v in g["arch"])
+    B, S, P = (int(v) for v in g["shape"])
+    m, ref = build_pair(d, H, Le, Ld, int(g["seed"]))
+    if sd_checksum(ref.state_dict()) != str(g["checksum"]):
+        pytest.skip("seeded init differs from the fixture's torch build")
+    tr = sdvg_b200.AdamTrainer(m, lr=float(g["lr"]), frames_to_predict=P, **CASES[tag])
+    w0 = {k: v.detach().clone() for k, v in ref.named_parameters()}
+    for step in range(2):
+        batch = OT.make_batch(B, S, E, seed=100 + step).to(DEV)
+        losses = tr.step(batch)
+        assert abs(float(losses[0]) - float(g[f"{tag}.loss{step}"])) <= 2e-5 * abs(float(g[f"{tag}.loss{step}"])), step
+        if step == 0:
+            pred = tr.prediction(B, S - 1)
+            want = g[f"{tag}.pred0"]
+            assert float((pred.cpu() - want).abs().max() / want.abs().max()) < 1e-4
+            for k, _ in ref.named_parameters():
+                got = tr.gradient(k)
+                amax = float(g[f"{tag}.g.{k}.amax"])
+                assert float((sample(got).cpu() - g[f"{tag}.g.{k}.s"]).abs().max()) <= TOLG * amax, k
+                assert abs(float(got.abs().max()) - amax) <= 2 * TOLG * amax, k
+                assert abs(float(got.double().sum()) - float(g[f"{tag}.g.{k}.sum"])) <= TOLG * amax * max(8.0, got.numel() ** 0.5), k
+    tr.pull_weights()
+    # Adam normalises every element by its own gradient magnitude, so elements whose gradient is tiny against the
+    # tensor's maximum amplify rounding differences: bound the error by a fraction of the step size (two steps
+    # move an element by up to 2 lr)
+    # (e.g. an attention's key bias, whose true gradient is zero: rounding noise becomes +-lr steps)
+    lr = float(g["lr"])
+    for k, p in m.named_parameters():
+        want = g[f"{tag}.w.{k}.s"]
+        assert float((want - sample(w0[k])).abs().max()) > 0.5 * lr, k             # the fixture did move this tensor
+        err = (sample(p).cpu() - want).abs()
+        big = g[f"{tag}.g.{k}.s"].abs() > 1e-2 * float(g[f"{tag}.g.{k}.amax"])
+        assert float(err.max()) <= 2.1 * lr, k
+        if big.any() and tag == "c5":     # smooth loss only: L1 / GDL(alpha 1) gradients are sign functions
+            assert float(err[big].max()) <= 0.5 * lr and float(err[big].mean()) <= 0.05 * lr, k
+
+
+def test_full_gradients_vs_oracle_and_partial_loss_window():
+    """Every element of every gradient against autograd of the oracle; frames_to_predict < S_tgt; B = 1."""
+    for (B, S, P, kw) in ((4, 6, 5, CASES["c5"]), (2, 6, 2, CASES["gdl1"]), (1, 4, 3, CASES["l1"])):
+        m, ref = build_pair(64, 2, 2, 2, seed=5)
+        tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=P, **kw)
+        opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
+        batch = OT.make_batch(B, S, 256, seed=7)
+        loss, pred, grads = OT.train_step_ref(ref, opt, batch, P, **kw)
+        losses = tr.step(batch.to(DEV))
+        assert abs(float(losses[0]) - float(loss)) <= 2e-5 * abs(float(loss))
+        for k, gr in grads.items():
+            got = tr.gradient(k).cpu()
+            assert float((got - gr).abs().max()) <= TOLG * float(gr.abs().max()) + 1e-12, (B, S, P, k)
+        tr.pull_weights()
+        for k, p in ref.named_parameters():       # first Adam step = lr * sign(g) wherever |g| >> eps: same sign, same step
+            err = (m.state_dict()[k].cpu() - p.detach()).abs()
+            big = grads[k].abs() > 1e-2 * grads[k].abs().max()
+            assert float(err.max()) <= 2.1e-5, k
+            if big.any():
+                assert float(err[big].max()) <= 1e-6, k
+
+
+def test_c5_architecture_step_vs_oracle():
+    """BASELINE config 5 (11_19_wallpushups_all_losses_test: d1024 H16 12e/12d, E=1024, batch 16, MSE + GDL(alpha 2) +
+    0.1 BiPatchNCE, Adam lr 1e-5) - one step on a reduced batch of 4 clips against the oracle."""
+    c = sdvg_b200.CONFIGS["11_19_wallpushups_all_losses_test"]
+    m, ref = build_pair(c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"], seed=0,
+                        frame_size=c["frame_size"])
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, **CASES["c5"])
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
+    batch = OT.make_batch(4, 6, 1024, seed=9)
+    loss, pred, grads = OT.train_step_ref(ref, opt, batch, 5, **CASES["c5"])
+    losses = tr.step(batch.to(DEV))
+    assert abs(float(losses[0]) - float(loss)) <= 2e-5 * abs(float(loss))
+    worst = 0.0
+    for k, gr in grads.items():
+        got = tr.gradient(k).cpu()
+        worst = max(worst, float((got - gr).abs().max() / gr.abs().max()))
+    assert worst <= TOLG, worst
+
+
+def test_data_parallel_shards_equal_global_batch():
+    """Two replicas, each with half of the clips and pe_index = global positions: the mean of their gradients is the
+    gradient of the global batch (what the NCCL all-reduce + 1/world Adam step computes), SURVEY.md 8(e)."""
+    kw = CASES["c5"]
+    B, S = 6, 6
+    batch = OT.make_batch(B, S, 256, seed=21)
+    m, ref = build_pair(64, 2, 1, 2, seed=6)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
+    _, _, grads = OT.train_step_ref(ref, opt, batch, 5, **kw)
+    shard_grads = []
+    for r in range(2):
+        mr, _ = build_pair(64, 2, 1, 2, seed=6)
+        tr = sdvg_b200.AdamTrainer(mr, lr=1e-5, frames_to_predict=5, **kw)
+        lo, hi = r * B // 2, (r + 1) * B // 2
+        tr.step(batch[lo:hi].to(DEV), pe_index=torch.arange(lo, hi))
+        shard_grads.append({k: tr.gradient(k).clone() for k in grads})
+    for k, gr in grads.items():
+        mean = 0.5 * (shard_grads[0][k] + shard_grads[1][k]).cpu()
+        assert float((mean - gr).abs().max()) <= TOLG * float(gr.abs().max()), k
+
+
+def test_16bit_training_mode_and_errors():
+    m, ref = build_pair(64, 2, 1, 1, seed=8, precision="mixed")
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, **CASES["l1"])
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
+    batch = OT.make_batch(3, 6, 256, seed=3)
+    loss, _, grads = OT.train_step_ref(ref, opt, batch, 5, **CASES["l1"])
+    losses = tr.step(batch.to(DEV))
+    assert abs(float(losses[0]) - float(loss)) <= 5e-3 * abs(float(loss))
+    for k, gr in grads.items():
+        assert float((tr.gradient(k).cpu() - gr).abs().max()) <= 2e-2 * float(gr.abs().max()), k
+    with pytest.raises(RuntimeError):
+        sdvg_b200.AdamTrainer(m, use_mse=True, use_L1=True)
+    with pytest.raises(RuntimeError):
+        tr.step(batch)                                                # CPU tensor
+    torch.manual_seed(0)
+    with pytest.raises(RuntimeError):
+        sdvg_b200.AdamTrainer(sdvg_b200.Transformer(0, 64, 2, 1, 1, 0.1, frame_size=64))     # dropout > 0
