@@ -105,21 +105,26 @@ def test_full_gradients_vs_oracle_and_partial_loss_window():
 
 def test_c5_architecture_step_vs_oracle():
     """BASELINE config 5 (11_19_wallpushups_all_losses_test: d1024 H16 12e/12d, E=1024, batch 16, MSE + GDL(alpha 2) +
-    0.1 BiPatchNCE, Adam lr 1e-5) - one step on a reduced batch of 4 clips against the oracle."""
+    0.1 BiPatchNCE, Adam lr 1e-5) - one step on a reduced batch of 4 clips.  At the far end of a 24-layer backward
+    chain the fp32 reference itself is 4e-4..8e-4 away from its float64 run (layer-0 attention, embedding), so the
+    yardstick is the float64 oracle: ours must be within 1e-4, or within 2x of the fp32 reference's own error."""
     c = sdvg_b200.CONFIGS["11_19_wallpushups_all_losses_test"]
-    m, ref = build_pair(c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"], seed=0,
-                        frame_size=c["frame_size"])
+    arch = (c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"])
+    m, ref = build_pair(*arch, seed=0, frame_size=c["frame_size"])
+    torch.manual_seed(0)
+    ref64 = RefTransformer(0, *arch, 0.0, frame_size=c["frame_size"]).double()
     tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, **CASES["c5"])
-    opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
     batch = OT.make_batch(4, 6, 1024, seed=9)
-    loss, pred, grads = OT.train_step_ref(ref, opt, batch, 5, **CASES["c5"])
+    loss, pred, grads = OT.train_step_ref(ref, torch.optim.Adam(ref.parameters(), lr=1e-5), batch, 5, **CASES["c5"])
+    _, _, grads64 = OT.train_step_ref(ref64, torch.optim.Adam(ref64.parameters(), lr=1e-5), batch.double(), 5, **CASES["c5"])
     losses = tr.step(batch.to(DEV))
     assert abs(float(losses[0]) - float(loss)) <= 2e-5 * abs(float(loss))
-    worst = 0.0
-    for k, gr in grads.items():
-        got = tr.gradient(k).cpu()
-        worst = max(worst, float((got - gr).abs().max() / gr.abs().max()))
-    assert worst <= TOLG, worst
+    assert float((tr.prediction(4, 5).cpu() - pred).abs().max() / pred.abs().max()) < 1e-4
+    for k, g64 in grads64.items():
+        scale = float(g64.abs().max())
+        ours = float((tr.gradient(k).cpu().double() - g64).abs().max()) / scale
+        ref32 = float((grads[k].double() - g64).abs().max()) / scale
+        assert ours <= max(TOLG, 2.0 * ref32), (k, ours, ref32)
 
 
 def test_data_parallel_shards_equal_global_batch():
