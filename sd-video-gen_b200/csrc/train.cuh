@@ -46,21 +46,28 @@ __global__ void __launch_bounds__(256) pack_t_kernel(const __grid_constant__ Pac
   if (row_end > limit) row_end = limit;
   float cs = 0.f;
   for (int r0 = row_begin; r0 < row_end; r0 += 128) {
-#pragma unroll 4
-    for (int rl = warp; rl < 128; rl += 8) {
-      const int r = r0 + rl;
-      float v = 0.f;
+    // all 16 row loads of this lane are issued before any is used (the kernel is latency-bound: 400 KB per launch)
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = r0 + warp + 8 * i;
+      v[i] = 0.f;
       if (r < a.R && c < a.C) {
         const int sr = a.perm_S > 0 ? (r % a.perm_S) * a.perm_B + r / a.perm_S : r;
-        v = __ldg(a.src + static_cast<size_t>(sr) * a.ld_src + c) * mul;
-        if (a.out_hi) {
-          const uint16_t h = to_plane_hi(v, a.bf16);
-          a.out_hi[static_cast<size_t>(r) * a.ld16 + c] = h;
-          if (a.out_lo) a.out_lo[static_cast<size_t>(r) * a.ld16 + c] = to_plane_lo(v, h);
-        }
+        v[i] = __ldg(a.src + static_cast<size_t>(sr) * a.ld_src + c);
       }
-      cs += v;
-      tile[lane][rl] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int rl = warp + 8 * i, r = r0 + rl;
+      const float x = v[i] * mul;
+      if (a.out_hi && r < a.R && c < a.C) {
+        const uint16_t h = to_plane_hi(x, a.bf16);
+        a.out_hi[static_cast<size_t>(r) * a.ld16 + c] = h;
+        if (a.out_lo) a.out_lo[static_cast<size_t>(r) * a.ld16 + c] = to_plane_lo(x, h);
+      }
+      cs += x;
+      tile[lane][rl] = x;
     }
     __syncthreads();
     if (a.t_hi) {
@@ -101,7 +108,7 @@ inline cudaError_t launch_pack_t(PackTArgs a, cudaStream_t stream) {
   if (a.t_hi && (a.Rpad % 4 != 0 || a.ld_t % 4 != 0)) return cudaErrorInvalidValue;
   const int limit = a.t_hi ? a.Rpad : a.R;
   // the column sums need every row in one CTA; otherwise split long matrices (weights) over the grid
-  a.rows_per_block = a.colsum ? ((limit + 127) / 128) * 128 : 512;
+  a.rows_per_block = a.colsum ? ((limit + 127) / 128) * 128 : 128;
   const dim3 grid(ceil_div(a.C, 32), ceil_div(limit, a.rows_per_block));
   return launch_kernel(pack_t_kernel, grid, dim3(256), 0, stream, a);
 }
@@ -191,6 +198,7 @@ struct AttnBwdArgs {
 };
 
 __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_constant__ AttnBwdArgs a) {
+  extern __shared__ float attn_bwd_smem[];   // per warp: Q[Sq][hd+1], dO[Sq][hd+1], K[Sk][hd+1], V[Sk][hd+1]
   __shared__ float sP[4][kTrainMaxS][kTrainMaxS];
   __shared__ float sD[4][kTrainMaxS][kTrainMaxS];
   pdl_wait();
@@ -199,28 +207,40 @@ __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_co
   const int wg = blockIdx.x * 4 + wib;
   if (wg >= a.clips * a.heads) return;
   const int b = wg / a.heads, h = wg - b * a.heads;
-  const int hd = a.hd, Sq = a.Sq, Sk = a.Sk;
+  const int hd = a.hd, Sq = a.Sq, Sk = a.Sk, ldp = hd + 1;
   const float* q = a.q + static_cast<size_t>(b) * Sq * a.ldq + h * hd;
   const float* k = a.k + static_cast<size_t>(b) * Sk * a.ldkv + h * hd;
   const float* v = a.v + static_cast<size_t>(b) * Sk * a.ldkv + h * hd;
   const float* dO = a.dO + static_cast<size_t>(b) * Sq * a.ld_do + h * hd;
+  float* sQ = attn_bwd_smem + static_cast<size_t>(wib) * (2 * Sq + 2 * Sk) * ldp;
+  float* sO = sQ + Sq * ldp;
+  float* sK = sO + Sq * ldp;
+  float* sV = sK + Sk * ldp;
   float (*P)[kTrainMaxS] = sP[wib];
   float (*D)[kTrainMaxS] = sD[wib];
-  for (int i = 0; i < Sq; ++i) {
-    for (int j = 0; j < Sk; ++j) {
-      float s = 0.f, dp = 0.f;
-      for (int e = lane; e < hd; e += 32) {
-        s = fmaf(__ldg(q + static_cast<size_t>(i) * a.ldq + e), __ldg(k + static_cast<size_t>(j) * a.ldkv + e), s);
-        dp = fmaf(__ldg(dO + static_cast<size_t>(i) * a.ld_do + e), __ldg(v + static_cast<size_t>(j) * a.ldkv + e), dp);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
-      if (lane == 0) {
-        const bool masked = a.causal && j > i + (Sk - Sq);
-        P[i][j] = masked ? -INFINITY : s * a.scale;
-        D[i][j] = dp;
-      }
+  // stage the four operands (all loads in flight together; rows are contiguous hd floats)
+  for (int i = 0; i < Sq; ++i)
+    for (int e = lane; e < hd; e += 32) {
+      sQ[i * ldp + e] = __ldg(q + static_cast<size_t>(i) * a.ldq + e);
+      sO[i * ldp + e] = __ldg(dO + static_cast<size_t>(i) * a.ld_do + e);
     }
+  for (int j = 0; j < Sk; ++j)
+    for (int e = lane; e < hd; e += 32) {
+      sK[j * ldp + e] = __ldg(k + static_cast<size_t>(j) * a.ldkv + e);
+      sV[j * ldp + e] = __ldg(v + static_cast<size_t>(j) * a.ldkv + e);
+    }
+  __syncwarp();
+  // scores and dP: one (query, key) pair per lane (row pitch hd+1: conflict-free)
+  for (int p = lane; p < Sq * Sk; p += 32) {
+    const int i = p / Sk, j = p - i * Sk;
+    float s = 0.f, dp = 0.f;
+    for (int e = 0; e < hd; ++e) {
+      s = fmaf(sQ[i * ldp + e], sK[j * ldp + e], s);
+      dp = fmaf(sO[i * ldp + e], sV[j * ldp + e], dp);
+    }
+    const bool masked = a.causal && j > i + (Sk - Sq);
+    P[i][j] = masked ? -INFINITY : s * a.scale;
+    D[i][j] = dp;
   }
   __syncwarp();
   if (lane < Sq) {
@@ -238,14 +258,14 @@ __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_co
   for (int e = lane; e < hd; e += 32) {
     for (int i = 0; i < Sq; ++i) {
       float acc = 0.f;
-      for (int j = 0; j < Sk; ++j) acc = fmaf(D[i][j], __ldg(k + static_cast<size_t>(j) * a.ldkv + e), acc);
+      for (int j = 0; j < Sk; ++j) acc = fmaf(D[i][j], sK[j * ldp + e], acc);
       a.dq[(static_cast<size_t>(b) * Sq + i) * a.ld_dq + h * hd + e] = acc * a.scale;
     }
     for (int j = 0; j < Sk; ++j) {
       float ak = 0.f, av = 0.f;
       for (int i = 0; i < Sq; ++i) {
-        ak = fmaf(D[i][j], __ldg(q + static_cast<size_t>(i) * a.ldq + e), ak);
-        av = fmaf(P[i][j], __ldg(dO + static_cast<size_t>(i) * a.ld_do + e), av);
+        ak = fmaf(D[i][j], sQ[i * ldp + e], ak);
+        av = fmaf(P[i][j], sO[i * ldp + e], av);
       }
       a.dk[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = ak * a.scale;
       a.dv[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = av;
@@ -255,7 +275,19 @@ __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_co
 
 inline cudaError_t launch_attention_backward(const AttnBwdArgs& a, cudaStream_t stream) {
   if (a.Sq > kTrainMaxS || a.Sk > kTrainMaxS) return cudaErrorInvalidValue;
-  return launch_kernel(attention_backward_kernel, dim3(ceil_div(a.clips * a.heads, 4)), dim3(128), 0, stream, a);
+  const size_t smem = 4 * static_cast<size_t>(2 * a.Sq + 2 * a.Sk) * (a.hd + 1) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 40 * 1024) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(attention_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set[dev & 63] = true;
+    }
+  }
+  return launch_kernel(attention_backward_kernel, dim3(ceil_div(a.clips * a.heads, 4)), dim3(128), smem, stream, a);
 }
 
 // ------------------------------------------------------------------------------------------------ criterion gradient

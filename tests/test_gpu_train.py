@@ -107,7 +107,7 @@ def test_c5_architecture_step_vs_oracle():
     """BASELINE config 5 (11_19_wallpushups_all_losses_test: d1024 H16 12e/12d, E=1024, batch 16, MSE + GDL(alpha 2) +
     0.1 BiPatchNCE, Adam lr 1e-5) - one step on a reduced batch of 4 clips.  At the far end of a 24-layer backward
     chain the fp32 reference itself is 4e-4..8e-4 away from its float64 run (layer-0 attention, embedding), so the
-    yardstick is the float64 oracle: ours must be within 1e-4, or within 2x of the fp32 reference's own error."""
+    yardstick is the float64 oracle: ours must be within 1e-4 plus twice the fp32 reference's own error."""
     c = sdvg_b200.CONFIGS["11_19_wallpushups_all_losses_test"]
     arch = (c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"])
     m, ref = build_pair(*arch, seed=0, frame_size=c["frame_size"])
@@ -124,7 +124,7 @@ def test_c5_architecture_step_vs_oracle():
         scale = float(g64.abs().max())
         ours = float((tr.gradient(k).cpu().double() - g64).abs().max()) / scale
         ref32 = float((grads[k].double() - g64).abs().max()) / scale
-        assert ours <= max(TOLG, 2.0 * ref32), (k, ours, ref32)
+        assert ours <= TOLG + 2.0 * ref32, (k, ours, ref32)
 
 
 def test_data_parallel_shards_equal_global_batch():
