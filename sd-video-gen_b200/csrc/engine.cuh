@@ -32,7 +32,7 @@ constexpr int kBoxRows[kNumBoxes] = {32, 64, 96, 128, 256};
 inline int box_index(int rows) { return rows == 32 ? 0 : rows == 64 ? 1 : rows == 96 ? 2 : rows == 128 ? 3 : 4; }
 
 // A GEMM tile plan: pair = CTA-pair kernel (256 x bn tiles) or one-CTA kernel (128 x bn tiles).
-struct TilePlan { bool pair; int bn; };
+struct TilePlan { bool pair; int bn; int ks = 1; };
 
 // 16-bit operand planes of a matrix [rows][cols] (row pitch ld, zero padded to a multiple of 64 columns so a
 // TMA box never leaves the tensor along K) with their tensor maps.
@@ -90,6 +90,9 @@ class Engine {
   std::vector<WeightSlot> slots;
   std::map<std::string, int> slot_of;
 
+  float* ks_ws = nullptr;            // split-K partial tiles of the small-M GEMMs (gemm_tc.cuh)
+  unsigned int* ks_flags = nullptr;
+  bool use_ksplit = false;           // SDVG_KSPLIT=1 enables: measured slower than one CTA per tile (profiles/README.md, round 1d)
   float* arena = nullptr;     // every fp32 parameter, in slot order
   size_t arena_count = 0;
 
@@ -387,6 +390,10 @@ class Engine {
         return fail_cuda(e, "cache alloc");
     }
     if (const char* v = std::getenv("SDVG_LAZY_LN")) lazy_ln = std::atoi(v) != 0;
+    if (const char* v = std::getenv("SDVG_KSPLIT")) use_ksplit = std::atoi(v) != 0;
+    if (tc() && ((e = dalloc(&ks_ws, static_cast<size_t>(num_sms) * kTcBM * 128)) != cudaSuccess ||
+                 (e = dalloc(&ks_flags, 1024)) != cudaSuccess))
+      return fail_cuda(e, "split-K workspace alloc");
     if ((e = dalloc(&ln_stats, static_cast<size_t>(max_rows))) != cudaSuccess) return fail_cuda(e, "stats alloc");
     std::vector<int> mod(c.max_clips);
     for (int i = 0; i < c.max_clips; ++i) mod[i] = i % 64;
@@ -477,7 +484,20 @@ class Engine {
   // ------------------------------------------------------------------ kernels
   // Tile plan: trade wave quantisation (tiles vs. SMs / SM pairs) against per-tile efficiency.  The relative
   // efficiencies are measured on B200 (tools/gpu_check.py gemm_speed, profiles/), normalised to the 256x256 pair tile.
-  TilePlan choose_plan(int M, int N, bool split) const {
+  TilePlan choose_plan(int M, int N, bool split, int K = 1 << 30) const {
+    if (K <= 256) {
+      // one or two K steps (the weight-gradient GEMMs of the training step, K = padded token count): the launch is
+      // all epilogue, so spread the output over as many SMs as possible - cost = rounds x tile width
+      TilePlan best{false, 32};
+      long best_cost = -1;
+      for (int bn : {32, 64, 128}) {
+        if (bn > 32 && bn > N) continue;
+        const long tiles = static_cast<long>(ceil_div(M, kTcBM)) * ceil_div(N, bn);
+        const long cost = ((tiles + num_sms - 1) / num_sms) * bn;
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = TilePlan{false, bn}; }
+      }
+      return best;
+    }
     // per-tile speed relative to the 256x256 pair tile, measured at 8192^3 on B200 (tools/gpu_check.py gemm_speed,
     // profiles/README.md): one-CTA 128 x {64,128,256}: 605 / 932 / 1171 TFLOP/s; pair 256 x {64,128,192,256}:
     // 678 / 991 / 1188 / 1337; split (3 MMAs per K step): pair 256x128 408-496, one-CTA 128x128 432.
@@ -510,6 +530,36 @@ class Engine {
     return best;
   }
 
+  // M <= 128 (small-batch rollouts, the training step): one row of 128 x bn tiles uses N / bn of the 148 SMs and each
+  // CTA walks the whole K extent.  Splitting K over `ks` CTAs per tile fills the machine - but measured on B200
+  // (tools/smallm_bench.py) a 96 x 1024 x 1024 GEMM is 6-9 us either way: the launch is fixed cost (prologue, first
+  // TMA round trip, epilogue, drain), and the partial-tile exchange adds 2-4 us.  Kept behind SDVG_KSPLIT=1, tested.
+  // Cost model (us): TMA round trips + bytes through one SM + epilogue + partial-tile exchange.
+  TilePlan choose_small_m(int M, int N, int K, bool split) const {
+    const int nk = ceil_div(K, kTcBK);
+    const int planes = split ? 2 : 1;
+    const int a_rows = kTcBM >> a_box_slot(M);
+    TilePlan best{false, 32, 1};
+    double best_cost = 1e300;
+    for (int bn : {32, 64, 128}) {
+      if (bn > 32 && bn > N) continue;
+      const int tiles = ceil_div(N, bn);
+      const int stage_bytes = planes * (kTcBM * kTcBK * 2 + bn * kTcBK * 2);
+      int stages = (kTcSmemLimit - 1024 - kTcEpiWarps * 32 * kTcEpiStride * 4 - 1024) / stage_bytes;
+      if (stages > 8) stages = 8;
+      for (int ks : {1, 2, 4, 8}) {
+        if (ks > 1 && (!use_ksplit || tiles * ks > num_sms || nk / ks < 2)) break;
+        const int kbs = ceil_div(nk, ks);
+        const double bytes = double(planes) * (a_rows + bn) * kTcBK * 2 * kbs;
+        const double rounds = ceil_div(tiles, num_sms);
+        const double cost = rounds * (ceil_div(kbs, stages) * 1.5 + bytes / 200e3 + 0.5 * bn / 32.0) +
+                            (ks > 1 ? 1.0 + 0.3 * (ks - 1) * bn / 32.0 : 0.0);
+        if (cost < best_cost) { best_cost = cost; best = TilePlan{false, bn, ks}; }
+      }
+    }
+    return best;
+  }
+
   // A-operand TMA box height for the one-CTA kernel: 128 rows, or 64 / 32 when the whole problem has fewer rows
   static int a_box_slot(int M) { return M <= 32 ? 2 : M <= 64 ? 1 : 0; }
 
@@ -517,6 +567,7 @@ class Engine {
                                cudaStream_t st) {
     TcGemmArgs args = args_in;
     args.a_box_rows = plan.pair ? kTcBM : (kTcBM >> a_box_slot(args.M));
+    if (!plan.pair && plan.ks > 1) { args.ksplit = plan.ks; if (!args.ks_ws) { args.ks_ws = ks_ws; args.ks_flags = ks_flags; } }
     const int bn = plan.bn;
     const int bi = box_index(plan.pair ? bn / 2 : bn);
     const int as = plan.pair ? 0 : a_box_slot(args.M);
@@ -560,7 +611,7 @@ class Engine {
       return launch_gemm_simt(A.f32, A.ld32, L.w32, L.K, M, L.N, L.K, e, st);
     }
     const bool split = L.split && A.p.lo != nullptr;
-    const TilePlan plan = choose_plan(M, L.N, split);
+    const TilePlan plan = (use_ksplit && M <= kTcBM && L.K > 256) ? choose_small_m(M, L.N, L.K, split) : choose_plan(M, L.N, split, L.K);
     TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, kTcBM, 0, nullptr, e};
     const double planes = split ? 2.0 : 1.0;
     Scope sc(this, KC_GEMM_TC, flops, 2.0 * planes * (double(M) * L.K + double(L.N) * L.K) + 4.0 * double(M) * L.N, st);

@@ -67,6 +67,12 @@ struct TcGemmArgs {
   int max_stages;             // 0 = all smem stages; >0 caps the TMA ring depth (pipeline experiments, SDVG_STAGES)
   unsigned long long* trace;  // optional [64] device buffer: CTA 0 records %globaltimer at pipeline events (tools/gemm_trace.py)
   Epilogue epi;
+  // split-K for small-M problems (one-CTA kernel, one tile per CTA group): `ksplit` consecutive CTAs share a tile,
+  // CTA r accumulates K blocks [r nk / ks, (r+1) nk / ks); r > 0 leave their fp32 partial tiles in ks_ws and bump
+  // ks_flags[tile], r == 0 waits, adds them in a fixed order (deterministic) and runs the fused epilogue.
+  int ksplit;
+  float* ks_ws;             // [tiles][ksplit-1][128][BN]
+  unsigned int* ks_flags;   // [tiles], zero between launches (reset by the last reader)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -161,6 +167,51 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmArgs& args, int
     epi_prefetch_chunk<FANCY>(args, row0, col_base + (c0 + j) * 32 + lc, lr, pre.b4[j], pre.res[j], pre.lw[j], pre.lb[j]);
 }
 
+// split-K: add the peers' partial sums of this lane's row (32 columns of chunk c) to the accumulator registers
+__device__ __forceinline__ void ks_add_partials(uint32_t (&r0)[32], const float* part_row, int kparts, int part_stride, int c) {
+  for (int p = 0; p < kparts; ++p) {
+    const float4* s4 = reinterpret_cast<const float4*>(part_row + static_cast<size_t>(p) * part_stride + c * 32);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 v = __ldcg(s4 + u);   // written by another SM during this launch: bypass L1
+      r0[4 * u] = __float_as_uint(__uint_as_float(r0[4 * u]) + v.x);
+      r0[4 * u + 1] = __float_as_uint(__uint_as_float(r0[4 * u + 1]) + v.y);
+      r0[4 * u + 2] = __float_as_uint(__uint_as_float(r0[4 * u + 2]) + v.z);
+      r0[4 * u + 3] = __float_as_uint(__uint_as_float(r0[4 * u + 3]) + v.w);
+    }
+  }
+}
+
+// split-K peer (rank > 0): dump this warp's 32 rows x NCW chunks of the accumulator as fp32 into the workspace
+template <int BN, bool SPLIT, int NCW, typename Release>
+__device__ __forceinline__ void tc_epilogue_partial(uint32_t tbase, int c0, int lane, float* dst_row, Release release) {
+#pragma unroll
+  for (int j = 0; j < NCW; ++j) {
+    const int c = c0 + j;
+    uint32_t r0[32];
+    ptx::tmem_ld_32x32b_x32(tbase + c * 32, r0);
+    if (SPLIT) {
+      uint32_t r1[32];
+      ptx::tmem_ld_32x32b_x32(tbase + BN + c * 32, r1);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(fmaf(__uint_as_float(r1[i]), kSplitInv, __uint_as_float(r0[i])));
+    } else {
+      ptx::tmem_ld_wait();
+    }
+    float4* d4 = reinterpret_cast<float4*>(dst_row + c * 32);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      __stcg(d4 + u, make_float4(__uint_as_float(r0[4 * u]), __uint_as_float(r0[4 * u + 1]), __uint_as_float(r0[4 * u + 2]),
+                                 __uint_as_float(r0[4 * u + 3])));
+  }
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) release();
+  __threadfence();
+  __syncwarp();
+}
+
 // Epilogue of one accumulator tile for one warp: 32 TMEM lanes (rows row0..row0+31) x NCW chunks of 32 columns
 // starting at chunk c0 of the tile whose first global column is col_base.  TMEM -> registers -> padded smem
 // transpose -> row-contiguous 128-bit global accesses.  `release()` is called by lane 0 once every TMEM read of
@@ -173,7 +224,8 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmArgs& args, int
 // buffer is addressed in the shared window explicitly.
 template <int BN, bool SPLIT, bool FANCY, int NCW, int PF, typename Release>
 __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* stg, uint32_t tbase, int row0,
-                                                 int col_base, int lane, int c0, EpiPre<PF>& pre, Release release) {
+                                                 int col_base, int lane, int c0, EpiPre<PF>& pre, Release release,
+                                                 const float* part_row = nullptr, int kparts = 0) {
   const Epilogue& e = args.epi;
   const int M = args.M, N = args.N;
   const uint32_t stg_addr = ptx::smem_u32(stg);
@@ -192,6 +244,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
       } else {
         ptx::tmem_ld_wait();
       }
+      if (kparts) ks_add_partials(r0, part_row, kparts, kTcBM * BN, c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(stg_addr + (lane * kTcEpiStride + 4 * j) * 4, r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
       if (c == c0 + NCW - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) release(); } else { __syncwarp(); }
@@ -237,6 +290,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
     } else {
       ptx::tmem_ld_wait();
     }
+    if (kparts) ks_add_partials(r0, part_row, kparts, kTcBM * BN, c);
 #pragma unroll
     for (int u = 0; u < 8; ++u) sts128(wr_addr + 16 * u, r0[4 * u], r0[4 * u + 1], r0[4 * u + 2], r0[4 * u + 3]);
     if (j == NCW - 1) {
@@ -336,6 +390,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kTcBK - 1) / kTcBK;
+  // split-K: `ks` consecutive CTAs share one tile (ks == 1: persistent over tiles as before)
+  const int ks = args.ksplit > 1 ? args.ksplit : 1;
+  const int cta = static_cast<int>(blockIdx.x) / ks, kr = static_cast<int>(blockIdx.x) - cta * ks;
+  const int ncta = static_cast<int>(gridDim.x) / ks;
+  const int kb0 = (num_kb * kr) / ks, kb1 = (num_kb * (kr + 1)) / ks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -371,9 +430,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t a_box_bytes = static_cast<uint32_t>((args.a_box_rows > 0 ? args.a_box_rows : kTcBM) * kTcBK * 2);
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cta; t < total_tiles; t += ncta) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sp = stage_base + stage * Cfg::kStageBytes;
         uint8_t* sb = sp + Cfg::kPlanes * Cfg::kABytes;
@@ -397,12 +456,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t phase = 0;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cta; t < total_tiles; t += ncta) {
       ptx::mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
       const uint32_t d1 = d0 + BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
@@ -414,7 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kTcBK / 16; ++k) {
-            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
             const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B = 2 << 4
             ptx::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
             if (SPLIT) {
@@ -423,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           ptx::umma_commit(&empty_bar[stage]);                         // smem stage reusable once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[buf]);     // accumulator(s) of this tile complete
+          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[buf]);        // accumulator(s) of this tile complete
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -442,17 +501,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     float* stg = epi_stage + (warp - 2) * 32 * kTcEpiStride;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles && active; t += gridDim.x) {
+    for (int t = cta; t < total_tiles && active; t += ncta) {
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
       const int row0 = m_blk * kTcBM + q * 32;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
+      uint64_t* done_bar = &tempty_bar[buf];
+      if (kr != 0) {
+        // split-K peer: fp32 partial tile -> workspace, then publish
+        ptx::mbar_wait(&tfull_bar[buf], buf_phase);
+        ptx::tc_fence_after();
+        float* dst = args.ks_ws + ((static_cast<size_t>(t) * (ks - 1) + (kr - 1)) * kTcBM + q * 32 + lane) * BN;
+        tc_epilogue_partial<BN, SPLIT, NCW>(tbase, c0, lane, dst, [done_bar]() { ptx::mbar_arrive(done_bar); });
+        if (lane == 0) atomicAdd(args.ks_flags + t, 1u);
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        continue;
+      }
       EpiPre<PF> pre;
       tc_epilogue_prefetch<FANCY, NCW, PF>(args, row0, n_blk * BN, lane, c0, pre);
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::kColsPerTile;
-      uint64_t* done_bar = &tempty_bar[buf];
+      const float* part_row = nullptr;
+      const unsigned int expected = static_cast<unsigned int>(Cfg::kEpiActive * (ks - 1));
+      if (ks > 1) {
+        // every peer warp has published its rows once the counter reaches kEpiActive * (ks - 1); all CTAs of the
+        // launch are co-resident (grid <= SM count, one CTA per SM), so the peers always make progress
+        if (lane == 0) {
+          const volatile unsigned int* f = args.ks_flags + t;
+          const long long t0 = clock64();
+          while (*f < expected) {
+            __nanosleep(40);
+            if (clock64() - t0 > 4000000000LL) { printf("sdvg gemm: split-K wait timed out (tile %d)\n", t); __trap(); }
+          }
+        }
+        __syncwarp();
+        __threadfence();
+        part_row = args.ks_ws + (static_cast<size_t>(t) * (ks - 1) * kTcBM + q * 32 + lane) * BN;
+      }
       tc_epilogue_tile<BN, SPLIT, FANCY, NCW, PF>(args, stg, tbase, row0, n_blk * BN, lane, c0, pre,
-                                                  [done_bar]() { ptx::mbar_arrive(done_bar); });
+                                                  [done_bar]() { ptx::mbar_arrive(done_bar); }, part_row, ks - 1);
+      if (ks > 1 && lane == 0) {
+        // the last reader of this tile's partials re-arms the flag for the next launch
+        if (atomicAdd(args.ks_flags + t, 1u) == expected + Cfg::kEpiActive - 1) args.ks_flags[t] = 0u;
+      }
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   }
@@ -525,7 +615,13 @@ inline cudaError_t launch_gemm_tc_f(const CUtensorMap& a_hi, const CUtensorMap& 
     attr_set[dev & 63] = true;
   }
   const int tiles = ceil_div(args.M, kTcBM) * ceil_div(args.N, BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (args.ksplit > 1) {
+    // split-K needs every CTA of the launch resident at once (rank 0 spins on its peers)
+    if (tiles * args.ksplit > num_sms || !args.ks_ws || !args.ks_flags || args.ksplit > ceil_div(args.K, kTcBK))
+      return cudaErrorInvalidConfiguration;
+    grid = tiles * args.ksplit;
+  }
   TcGemmArgs a2 = args;
   a2.vec4 = epilogue_vec4_ok(args.epi, args.N) ? 1 : 0;
   return launch_kernel(gemm_tc_kernel<BN, SPLIT, FANCY>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, a_hi, a_lo, b_hi, b_lo, a2);

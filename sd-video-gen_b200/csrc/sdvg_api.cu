@@ -237,7 +237,23 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     Engine tmp_eng;
     tmp_eng.num_sms = prop.multiProcessorCount;
     tmp_eng.cfg.precision = precision;
-    TilePlan plan = block_n == 0 ? tmp_eng.choose_plan(M, N, split) : TilePlan{block_n < 0, block_n < 0 ? -block_n : block_n};
+    // block_n >= 1000 (tests): split-K factor block_n / 1000 with tile width block_n % 1000 (one-CTA kernel, M <= 128)
+    int force_ks = 1;
+    if (block_n >= 1000) { force_ks = block_n / 1000; block_n %= 1000; }
+    TilePlan plan = block_n == 0 ? (std::getenv("SDVG_KSPLIT") && std::atoi(std::getenv("SDVG_KSPLIT")) && M <= kTcBM && K > 256
+                                     ? (tmp_eng.use_ksplit = true, tmp_eng.choose_small_m(M, N, K, split)) : tmp_eng.choose_plan(M, N, split, K))
+                                 : TilePlan{block_n < 0, block_n < 0 ? -block_n : block_n, force_ks};
+    if (plan.ks > 1) {
+      void *w = nullptr, *f = nullptr;
+      const size_t wbytes = static_cast<size_t>(prop.multiProcessorCount) * kTcBM * 128 * sizeof(float);
+      if (cudaMalloc(&w, wbytes) != cudaSuccess || cudaMalloc(&f, 4096) != cudaSuccess) {
+        if (w) cudaFree(w);
+        cleanup(); g_create_error = "sdvg_gemm: out of device memory"; return SDVG_ERR_CUDA;
+      }
+      tmp.push_back(w); tmp.push_back(f);
+      cudaMemsetAsync(f, 0, 4096, st);
+      tmp_eng.ks_ws = static_cast<float*>(w); tmp_eng.ks_flags = static_cast<unsigned int*>(f);
+    }
     const int bn = plan.bn;
     const bool ok1 = !plan.pair && (bn == 32 || bn == 64 || bn == 128 || bn == 256) && !(split && bn == 256) && !(bn > N && bn > 32);
     const bool ok2 = plan.pair && (bn == 64 || bn == 128 || bn == 192 || bn == 256) && !(split && bn > 128) && bn / 2 <= N;

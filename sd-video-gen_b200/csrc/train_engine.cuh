@@ -75,6 +75,21 @@ class Trainer {
   float *gA = nullptr, *gB = nullptr, *gWide = nullptr, *gAttn = nullptr, *gQc = nullptr, *gKvc = nullptr, *gMem = nullptr,
         *gEmbT = nullptr;
 
+  // The weight-gradient branch of every linear layer (pack_xt + dW GEMM) runs on a side stream next to the
+  // activation-gradient chain (dX GEMM, LayerNorm / attention backward): both are small launches that fill a
+  // fraction of the SMs.  ev_dy: dY planes ready (main -> side); ev_side: side finished with dAT / XT (side -> main).
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_dy = nullptr, ev_side = nullptr, ev_fwd = nullptr;
+  bool side_pending = false;
+  bool use_side = true;     // SDVG_TRAIN_STREAMS=0 keeps everything on the caller's stream
+
+  ~Trainer() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_dy) cudaEventDestroy(ev_dy);
+    if (ev_side) cudaEventDestroy(ev_side);
+    if (ev_fwd) cudaEventDestroy(ev_fwd);
+  }
+
   // ------------------------------------------------------------------ set-up
   int slot_containing(const float* p) const {
     for (size_t i = 0; i < g.slots.size(); ++i)
@@ -185,6 +200,14 @@ class Trainer {
     if (!g.map_planes(dAT.p, false) || !g.map_planes(XT.p, true) || !g.map_planes(XTmem.p, true))
       return g.fail(SDVG_ERR_CUDA, "tensor map creation failed (transposed operands)");
     XT.split = lo; XTmem.split = lo;
+    if (const char* v = std::getenv("SDVG_TRAIN_STREAMS")) use_side = std::atoi(v) != 0;
+    if (use_side) {
+      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_dy, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_fwd, cudaEventDisableTiming) != cudaSuccess)
+        return g.fail(SDVG_ERR_CUDA, "stream / event creation failed");
+    }
     ready = true;
     wt_stale = true;
     return SDVG_OK;
@@ -294,11 +317,37 @@ class Trainer {
   // full backward of one linear layer whose input x (fp32, saved) has M rows
   cudaError_t linear_bwd(const TLinear& tl, const float* dy, int ld_dy, const float* x, int M, float* dx, const float* residual,
                          cudaStream_t st, const float* gate = nullptr, int ld_gate = 0, Linear* xt_ready = nullptr) {
+    SDVG_CK(weight_branch_begin(st));
     SDVG_CK(pack_dy(dy, ld_dy, M, tl.fwd.N, tl.gb, false, st));
-    if (!xt_ready) SDVG_CK(pack_xt(x, tl.fwd.K, M, tl.fwd.K, XT, st));
-    SDVG_CK(grad_w(tl.fwd.N, tl.fwd.K, M, tl.gw, false, xt_ready ? *xt_ready : XT, st));
+    SDVG_CK(weight_branch(tl.fwd.N, tl.fwd.K, M, tl.gw, false, xt_ready ? nullptr : x, tl.fwd.K, xt_ready ? *xt_ready : XT, st));
     if (dx) SDVG_CK(grad_x(tl, M, dx, residual, gate, ld_gate, st));
     return cudaSuccess;
+  }
+  // before dAT is overwritten: the side stream must be done with the previous layer's dW GEMM
+  cudaError_t weight_branch_begin(cudaStream_t st) {
+    if (side && side_pending) { SDVG_CK(cudaStreamWaitEvent(st, ev_side, 0)); side_pending = false; }
+    return cudaSuccess;
+  }
+  // pack_xt (unless the transposed operand is already there) + dW GEMM, on the side stream when enabled
+  cudaError_t weight_branch(int N, int K, int M, float* gw, bool accumulate, const float* x, int ld_x, Linear& xt, cudaStream_t st) {
+    cudaStream_t ws = side ? side : st;
+    if (side) { SDVG_CK(cudaEventRecord(ev_dy, st)); }
+    if (x) SDVG_CK(pack_xt(x, ld_x, M, K, xt, ws));
+    if (side) SDVG_CK(cudaStreamWaitEvent(side, ev_dy, 0));
+    SDVG_CK(grad_w(N, K, M, gw, accumulate, xt, ws));
+    if (side) { SDVG_CK(cudaEventRecord(ev_side, side)); side_pending = true; }
+    return cudaSuccess;
+  }
+  // the caller's stream waits for everything the side stream still has in flight
+  cudaError_t weight_branch_join(cudaStream_t st) {
+    if (side && side_pending) { SDVG_CK(cudaStreamWaitEvent(st, ev_side, 0)); side_pending = false; }
+    return cudaSuccess;
+  }
+  // the side stream may not start before the forward pass (saved activations, loss scale) is complete
+  cudaError_t weight_branch_fork(cudaStream_t st) {
+    if (!side) return cudaSuccess;
+    SDVG_CK(cudaEventRecord(ev_fwd, st));
+    return cudaStreamWaitEvent(side, ev_fwd, 0);
   }
 
   // ------------------------------------------------------------------ forward with saved activations
@@ -433,9 +482,10 @@ class Trainer {
     const int B = Bc, Ss = Ssc, St = Stc, Ms = B * Ss, Mt = B * St;
     const int Ld = static_cast<int>(g.dec.size());
     // out projection: dpred is (S_tgt, B, E) and unscaled -> clip-major rows, multiplied by the loss scale
+    SDVG_CK(weight_branch_fork(st));
+    SDVG_CK(weight_branch_begin(st));
     SDVG_CK(pack_dy(dpred, E, Mt, E, t_out.gb, false, st, 1.0f, scale, St, B));
-    SDVG_CK(pack_xt(fin32, d, Mt, d, XT, st));
-    SDVG_CK(grad_w(E, d, Mt, t_out.gw, false, XT, st));
+    SDVG_CK(weight_branch(E, d, Mt, t_out.gw, false, fin32, d, XT, st));
     SDVG_CK(grad_x(t_out, Mt, gA, nullptr, nullptr, 0, st));
     SDVG_CK(ln_bwd(gA, xd[Ld], st_dec, g.dec_norm, g_decnorm, Mt, gB, st));
     float* gin = gB;    // gradient w.r.t. the current layer's output
@@ -452,7 +502,7 @@ class Trainer {
       SDVG_CK(linear_bwd(T.ca.out, gtmp, d, s.ac, Mt, gAttn, nullptr, st));              // gAttn = d(attention output)
       SDVG_CK(attention_bwd(s.qc, d, s.kvc, s.kvc + d, 2 * d, gAttn, gQc, d, gKvc, gKvc + d, 2 * d, B, St, Ss, 0, st));
       SDVG_CK(linear_bwd(T.ca.q, gQc, d, s.x1, Mt, gin, gtmp, st));                      // gin = dx1 = dq Wq + dy2
-      if (l == Ld - 1) SDVG_CK(pack_xt(mem32, d, Ms, d, XTmem, st));
+      if (l == Ld - 1) SDVG_CK(pack_xt(mem32, d, Ms, d, XTmem, st));   // main stream: ordered before every later ev_dy
       SDVG_CK(linear_bwd(T.ca.kv, gKvc, 2 * d, nullptr, Ms, gMem, mem_started ? gMem : nullptr, st, nullptr, 0, &XTmem));
       mem_started = true;
       // x1 = LN1(y1), y1 = x + SA(x)
@@ -462,6 +512,7 @@ class Trainer {
                             St, 1, st));
       SDVG_CK(linear_bwd(T.sa.qkv, gWide, 3 * d, xd[l], Mt, l == 0 ? gEmbT : gin, gtmp, st));   // dx = dqkv Wqkv + dy1
     }
+    SDVG_CK(weight_branch_join(st));
     if (Ld == 0) {
       SDVG_CK(cudaMemcpyAsync(gEmbT, gB, static_cast<size_t>(Mt) * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
       SDVG_CK(cudaMemsetAsync(gMem, 0, static_cast<size_t>(Ms) * d * sizeof(float), st));
@@ -475,9 +526,10 @@ class Trainer {
     const int Le = static_cast<int>(g.enc.size());
     const float sqrt_d = sqrtf(static_cast<float>(d));
     // target embedding: emb = (x W^T + b) sqrt(d) + PE
+    SDVG_CK(weight_branch_fork(st));
+    SDVG_CK(weight_branch_begin(st));
     SDVG_CK(pack_dy(gEmbT, d, Mt, d, t_emb.gb, false, st, sqrt_d, nullptr, 0, 0, false));
-    SDVG_CK(pack_xt(tgt_c, E, Mt, E, XT, st));
-    SDVG_CK(grad_w(d, E, Mt, t_emb.gw, false, XT, st));
+    SDVG_CK(weight_branch(d, E, Mt, t_emb.gw, false, tgt_c, E, XT, st));
     // encoder.norm
     SDVG_CK(ln_bwd(gMem, xe[Le], st_enc, g.enc_norm, g_encnorm, Ms, gB, st));
     float* gin = gB;
@@ -494,10 +546,10 @@ class Trainer {
       SDVG_CK(linear_bwd(T.sa.qkv, gWide, 3 * d, xe[l], Ms, gin, gtmp, st));             // dx
     }
     // source embedding (same weights as the target embedding: accumulate)
+    SDVG_CK(weight_branch_begin(st));
     SDVG_CK(pack_dy(gin, d, Ms, d, t_emb.gb, true, st, sqrt_d, nullptr, 0, 0, false));
-    SDVG_CK(pack_xt(src_c, E, Ms, E, XT, st));
-    SDVG_CK(grad_w(d, E, Ms, t_emb.gw, true, XT, st));
-    return cudaSuccess;
+    SDVG_CK(weight_branch(d, E, Ms, t_emb.gw, true, src_c, E, XT, st));
+    return weight_branch_join(st);
   }
 
   // forward + criterion + backward.  part 0: everything; 1: up to and including the decoder backward; 2: the rest.

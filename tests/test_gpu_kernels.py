@@ -72,3 +72,27 @@ def test_gemm_linearity():
     c1 = sdvg_b200.gemm(A, W, None, precision="fp32")[0]
     c2 = sdvg_b200.gemm(2.0 * A, W, None, precision="fp32")[0]      # power-of-two scaling is exact in every plane
     assert torch.equal(c2, 2.0 * c1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_split_k_small_m_gemm(precision):
+    """M <= 128 GEMMs split K over 2/4/8 CTAs per tile (partial tiles exchanged through L2, summed in a fixed
+    order): same result as the float64 reference, deterministic from launch to launch, flags re-armed between
+    launches (iters > 1 reuses them), ragged M / N, bias + ReLU in the fused epilogue of rank 0."""
+    import sdvg_b200
+    for (M, N, K) in ((96, 1024, 1024), (40, 1024, 2048), (128, 512, 1024), (80, 3072, 1024), (5, 200, 512)):
+        g = torch.Generator(device="cuda").manual_seed(M + N)
+        A = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+        b = torch.randn(N, device="cuda", generator=g)
+        want = ref(A, W, b, True, precision)
+        for bn, ks in ((32, 4), (32, 2), (64, 2), (32, 8), (128, 4), (64, 4)):
+            tiles = -(-N // bn)
+            if tiles * ks > 148 or (K // 64) // ks < 1:
+                continue
+            C1, _ = sdvg_b200.gemm(A, W, b, relu=True, precision=precision, block_n=1000 * ks + bn)
+            C2, _ = sdvg_b200.gemm(A, W, b, relu=True, precision=precision, block_n=1000 * ks + bn, iters=3)
+            assert relerr(C1, want) < TOL[precision], (M, N, K, bn, ks)
+            assert torch.equal(C1, C2), (M, N, K, bn, ks)
+        C0, _ = sdvg_b200.gemm(A, W, b, relu=True, precision=precision)            # automatic plan (split-K when it pays)
+        assert relerr(C0, want) < TOL[precision], (M, N, K)

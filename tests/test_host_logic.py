@@ -137,3 +137,51 @@ def test_sibling_modules_on_cpu():
     x = torch.arange(24.0).view(2, 3, 4)
     assert torch.equal(ident(x, x), x[:, -1:])                       # models/identity.py:13-16
     assert torch.equal(ident.get_tgt_mask(4), m.get_tgt_mask(4))
+
+
+def _dp_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle import functional as F
+    from oracle import losses as L
+    from oracle.ref_module import RefTransformer
+    from oracle.train import make_batch
+    torch.manual_seed(4)
+    ref = RefTransformer(0, 32, 4, 1, 1, 0.0, frame_size=64)
+    names = [k for k, _ in ref.named_parameters()]
+    sd = {k: v.detach().clone().requires_grad_(k in names) for k, v in ref.state_dict().items()}
+    kw = dict(use_mse=True, use_L1=False, use_gdl=True, lambda_gdl=1, alpha=2, use_contrastive=True, temperature=0.07,
+              lambda_contrastive=0.1)
+    batch = make_batch(6, 6, 256, seed=12)
+
+    def grads_of(x, pe):
+        for k in names:
+            sd[k].grad = None
+        pred = F.forward(sd, x, x[:, :-1], 4, F.causal_mask(5), pe_index=pe)
+        L.criterion(**kw)(pred, x[:, 1:].permute(1, 0, 2)).backward()
+        return torch.cat([sd[k].grad.reshape(-1) for k in names])
+
+    per = 6 // world
+    flat = grads_of(batch[rank * per:(rank + 1) * per], torch.arange(rank * per, (rank + 1) * per))   # this rank's shard
+    split = flat.numel() // 3
+    for w in sdvg_b200.allreduce_buckets(flat, split, world):
+        w.wait()
+    flat /= world                                               # what sdvg_train_adam_step's grad_mul = 1/world applies
+    if rank == 0:
+        torch.save((flat, grads_of(batch, torch.arange(6))), tmp)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_buckets_gloo(tmp_path):
+    """world_size-2 gloo: the two-bucket sum all-reduce of the flat gradient vector followed by 1/world equals the
+    gradient of the global batch (equal shards, mean-reduced losses, pe_index = global clip positions) - the host
+    logic of AdamTrainer.step, SURVEY.md section 8e."""
+    tmp = str(tmp_path / "dp.pt")
+    mp.spawn(_dp_worker, args=(2, 29543, tmp), nprocs=2, join=True)
+    got, want = torch.load(tmp)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
