@@ -193,6 +193,13 @@ int sdvg_train_backward(sdvg_handle* h, const float* src, const float* tgt, cons
  * buffer a data-parallel trainer hands to ncclAllReduce (torch.distributed.all_reduce on a tensor view of it). */
 int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t* decoder_offset);
 
+/* Finer-grained overlap: while sdvg_train_backward enqueues the backward pass it calls `fn(user, offset, count)` (on
+ * the calling host thread) each time a range of the flat gradient vector is final given the work enqueued so far on
+ * `stream` - from the end of the vector to its start, every `layers_per_bucket` layers; the ranges tile the vector.
+ * The caller records an event on `stream` there and starts that range's all-reduce on its own stream.  NULL clears. */
+typedef void (*sdvg_grad_ready_fn)(void* user, long long offset, long long count);
+int sdvg_train_set_ready_callback(sdvg_handle* h, sdvg_grad_ready_fn fn, void* user, int32_t layers_per_bucket);
+
 /* Offset / element count of a state_dict entry inside the flat parameter (and gradient) vector. */
 int sdvg_param_range(const sdvg_handle* h, const char* key, int64_t* offset, int64_t* count);
 

@@ -15,7 +15,7 @@ SYMBOLS = (
     "sdvg_version", "sdvg_last_error", "sdvg_create", "sdvg_destroy", "sdvg_workspace_bytes", "sdvg_set_weight",
     "sdvg_num_weights", "sdvg_weight_key", "sdvg_finalize_weights", "sdvg_forward", "sdvg_rollout",
     "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm", "sdvg_criterion",
-    "sdvg_train_backward", "sdvg_train_gradients", "sdvg_param_range", "sdvg_train_prediction", "sdvg_train_adam_step",
+    "sdvg_train_backward", "sdvg_train_gradients", "sdvg_train_set_ready_callback", "sdvg_param_range", "sdvg_train_prediction", "sdvg_train_adam_step",
     "sdvg_get_weight",
 )
 
@@ -32,6 +32,8 @@ class SdvgLossConfig(C.Structure):
                 ("lambda_gdl", C.c_float), ("alpha", C.c_float), ("use_contrastive", C.c_int32),
                 ("temperature", C.c_float), ("lambda_contrastive", C.c_float)]
 
+
+GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_longlong, C.c_longlong)
 
 _lib = None
 
@@ -76,6 +78,7 @@ def load(build_if_missing=True):
     lib.sdvg_criterion.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, vp, vp]
     lib.sdvg_train_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.POINTER(SdvgLossConfig), vp, vp, i32, vp]
     lib.sdvg_train_gradients.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sdvg_train_set_ready_callback.argtypes = [vp, GRAD_READY_FN, vp, i32]
     lib.sdvg_param_range.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.sdvg_train_prediction.argtypes = [vp, C.POINTER(vp)]
     lib.sdvg_train_adam_step.argtypes = [vp, f32, f32, f32, f32, f32, vp]

@@ -152,6 +152,15 @@ int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t*
   return SDVG_OK;
 }
 
+int sdvg_train_set_ready_callback(sdvg_handle* h, sdvg_grad_ready_fn fn, void* user, int32_t layers_per_bucket) {
+  if (!h) return SDVG_ERR_INVALID;
+  sdvg::Trainer* t = trainer_of(h);
+  if (!t) return h->eng.fail(SDVG_ERR_INVALID, "out of host memory");
+  t->ready_cb = fn; t->ready_user = user;
+  t->layers_per_bucket = layers_per_bucket > 0 ? layers_per_bucket : 3;
+  return SDVG_OK;
+}
+
 int sdvg_param_range(const sdvg_handle* h, const char* key, int64_t* offset, int64_t* count) {
   if (!h) return SDVG_ERR_INVALID;
   auto it = h->eng.slot_of.find(key ? key : "");

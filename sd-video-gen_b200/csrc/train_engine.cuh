@@ -90,6 +90,26 @@ class Trainer {
     if (ev_fwd) cudaEventDestroy(ev_fwd);
   }
 
+  // Gradient-ready notifications for a data-parallel caller: while the backward pass is being enqueued, `ready_cb`
+  // is called with consecutive ranges [offset, offset + count) of the flat gradient vector whose values are final
+  // once the work enqueued so far on the stream has run (the caller records an event there and starts the
+  // all-reduce of that range on its communication stream).  Ranges arrive from the end of the vector to its start
+  // and tile it exactly; a range covers `layers_per_bucket` layers.
+  typedef void (*ReadyFn)(void* user, long long offset, long long count);
+  ReadyFn ready_cb = nullptr;
+  void* ready_user = nullptr;
+  int layers_per_bucket = 3;
+  size_t ready_hi = 0;       // everything in [ready_hi, arena_count) has been announced
+
+  cudaError_t announce(size_t lo, cudaStream_t st) {
+    if (!ready_cb || lo >= ready_hi) return cudaSuccess;
+    SDVG_CK(weight_branch_join(st));     // the weight gradients of these layers come from the side stream
+    ready_cb(ready_user, static_cast<long long>(lo), static_cast<long long>(ready_hi - lo));
+    ready_hi = lo;
+    return cudaSuccess;
+  }
+  size_t offset_of(const float* p) const { return static_cast<size_t>(p - g.arena); }
+
   // ------------------------------------------------------------------ set-up
   int slot_containing(const float* p) const {
     for (size_t i = 0; i < g.slots.size(); ++i)
@@ -482,6 +502,7 @@ class Trainer {
     const int B = Bc, Ss = Ssc, St = Stc, Ms = B * Ss, Mt = B * St;
     const int Ld = static_cast<int>(g.dec.size());
     // out projection: dpred is (S_tgt, B, E) and unscaled -> clip-major rows, multiplied by the loss scale
+    ready_hi = g.arena_count;
     SDVG_CK(weight_branch_fork(st));
     SDVG_CK(weight_branch_begin(st));
     SDVG_CK(pack_dy(dpred, E, Mt, E, t_out.gb, false, st, 1.0f, scale, St, B));
@@ -511,8 +532,10 @@ class Trainer {
       SDVG_CK(attention_bwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, gAttn, gWide, 3 * d, gWide + d, gWide + 2 * d, 3 * d, B, St,
                             St, 1, st));
       SDVG_CK(linear_bwd(T.sa.qkv, gWide, 3 * d, xd[l], Mt, l == 0 ? gEmbT : gin, gtmp, st));   // dx = dqkv Wqkv + dy1
+      if (l == 0 || (Ld - l) % layers_per_bucket == 0) SDVG_CK(announce(offset_of(L.sa.qkv.w32), st));
     }
     SDVG_CK(weight_branch_join(st));
+    SDVG_CK(announce(decoder_offset, st));
     if (Ld == 0) {
       SDVG_CK(cudaMemcpyAsync(gEmbT, gB, static_cast<size_t>(Mt) * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
       SDVG_CK(cudaMemsetAsync(gMem, 0, static_cast<size_t>(Ms) * d * sizeof(float), st));
@@ -544,12 +567,14 @@ class Trainer {
       SDVG_CK(attention_bwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, gAttn, gWide, 3 * d, gWide + d, gWide + 2 * d, 3 * d, B, Ss,
                             Ss, 0, st));
       SDVG_CK(linear_bwd(T.sa.qkv, gWide, 3 * d, xe[l], Ms, gin, gtmp, st));             // dx
+      if (l == 0 || (Le - l) % layers_per_bucket == 0) SDVG_CK(announce(offset_of(L.sa.qkv.w32), st));
     }
     // source embedding (same weights as the target embedding: accumulate)
     SDVG_CK(weight_branch_begin(st));
     SDVG_CK(pack_dy(gin, d, Ms, d, t_emb.gb, true, st, sqrt_d, nullptr, 0, 0, false));
     SDVG_CK(weight_branch(d, E, Ms, t_emb.gw, true, src_c, E, XT, st));
-    return weight_branch_join(st);
+    SDVG_CK(weight_branch_join(st));
+    return announce(0, st);
   }
 
   // forward + criterion + backward.  part 0: everything; 1: up to and including the decoder backward; 2: the rest.

@@ -127,7 +127,7 @@ class AdamTrainer:
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, *, frames_to_predict=5, use_mse=True, use_L1=False,
                  use_gdl=True, lambda_gdl=1, alpha=2, use_contrastive=True, temperature=0.07, lambda_contrastive=0.1,
-                 overlap=True, ignore_dropout=False):
+                 overlap=True, layers_per_bucket=3, ignore_dropout=False):
         if use_mse and use_L1:
             raise RuntimeError("Invalid loss function combination")        # trainers/trainer.py:107-109
         if getattr(model, "dropout_p", 0.0) > 0 and not ignore_dropout:
@@ -138,7 +138,9 @@ class AdamTrainer:
                                             float(lambda_gdl), float(alpha), int(bool(use_contrastive)), float(temperature),
                                             float(lambda_contrastive))
         self.overlap = overlap
+        self.layers_per_bucket = int(layers_per_bucket)
         self._comm_stream = None
+        self._cb = None
         self.steps = 0
 
     # -- views of library-owned memory
@@ -201,16 +203,29 @@ class AdamTrainer:
         else:
             flat, split = self.gradients(device)
             if self.overlap:
+                # the library announces gradient ranges as the backward pass is enqueued (sdvg_train_set_ready_callback):
+                # each range is all-reduced on the communication stream while the rest of the backward still runs
                 if self._comm_stream is None:
                     self._comm_stream = torch.cuda.Stream(device)
-                backward(1)
-                self._comm_stream.wait_stream(stream)
-                with torch.cuda.stream(self._comm_stream):
-                    w1 = dist.all_reduce(flat[split:], op=dist.ReduceOp.SUM, async_op=True)
-                backward(2)
-                w1.wait()                                  # orders the current stream after the first bucket's reduction
-                stream.wait_stream(self._comm_stream)
-                dist.all_reduce(flat[:split], op=dist.ReduceOp.SUM)
+                works = []
+                comm = self._comm_stream
+
+                def ready(_user, off, cnt):
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    comm.wait_event(ev)
+                    with torch.cuda.stream(comm):
+                        works.append(dist.all_reduce(flat[off:off + cnt], op=dist.ReduceOp.SUM, async_op=True))
+
+                self._cb = _lib.GRAD_READY_FN(ready)          # keep the ctypes thunk alive while the library holds it
+                _lib.check(lib.sdvg_train_set_ready_callback(h, self._cb, None, self.layers_per_bucket), h)
+                try:
+                    backward(0)
+                finally:
+                    _lib.check(lib.sdvg_train_set_ready_callback(h, _lib.GRAD_READY_FN(0), None, 0), h)
+                for w in works:
+                    w.wait()                                # orders the current stream after each range's reduction
+                stream.wait_stream(comm)
             else:
                 backward(0)
                 for w in allreduce_buckets(flat, split, world):
