@@ -165,8 +165,8 @@ int sdvg_criterion(int32_t device, const float* pred, const float* target, int32
  * Training step - replaces the body of Trainer.train_loop (trainers/trainer.py:123-165): teacher-forced forward
  * model(new_batch, y_input, tgt_mask) (:141), criterion on the last frames_to_predict positions (:145),
  * opt.zero_grad(); loss.backward(); opt.step() (:160-162) with opt = Adam(model.parameters(), lr) (:365).
- * The handle must use a tensor-core precision (SDVG_FP32 for <=1e-4 gradient parity).  Dropout is the identity
- * (the reference's DROPOUT_P uses torch's RNG stream; parity is defined for dropout_p = 0). */
+ * The handle must use a tensor-core precision (SDVG_FP32 for <=1e-4 gradient parity).  Dropout is off unless
+ * sdvg_train_set_dropout is called. */
 typedef struct sdvg_loss_config {   /* arguments of Trainer.criterion, trainers/trainer.py:88 */
   int32_t frames_to_predict;        /* P: loss over pred[-P:], y_expected[-P:] (:145) */
   int32_t use_mse, use_l1, use_gdl;
@@ -192,6 +192,14 @@ int sdvg_train_backward(sdvg_handle* h, const float* src, const float* tgt, cons
 /* The flat gradient vector (device fp32, `count` elements) and the offset of the decoder-side bucket.  This is the
  * buffer a data-parallel trainer hands to ncclAllReduce (torch.distributed.all_reduce on a tensor view of it). */
 int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t* decoder_offset);
+
+/* Training-mode dropout with probability p (DROPOUT_P of the reference's configs) at nn.Transformer's sites: the
+ * embedding + positional sum (models/positional_encoding.py:35), the attention probabilities, every sub-layer output
+ * before its residual add and the FFN hidden activation.  Masks are a counter-based hash of (seed, training step,
+ * site, element index) - csrc/common.cuh drop_hash, restated in oracle/dropout.py - regenerated in the backward pass.
+ * torch's own Philox stream is NOT reproduced: with p > 0 a run is statistically, not bitwise, comparable to the
+ * reference; parity tests feed the same masks to the oracle.  p = 0 (default) disables. */
+int sdvg_train_set_dropout(sdvg_handle* h, float p, uint64_t seed);
 
 /* Finer-grained overlap: while sdvg_train_backward enqueues the backward pass it calls `fn(user, offset, count)` (on
  * the calling host thread) each time a range of the flat gradient vector is final given the work enqueued so far on

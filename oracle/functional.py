@@ -49,8 +49,13 @@ def layer_norm(x, w, b):
     return (x - mean) / torch.sqrt(var + LN_EPS) * w + b
 
 
-def mha(q_in, kv_in, sd, prefix, n_heads, mask, operand):
-    """q_in (B,Sq,d), kv_in (B,Sk,d); mask (Sq,Sk) additive or None."""
+def _no_drop(site, x):
+    return x
+
+
+def mha(q_in, kv_in, sd, prefix, n_heads, mask, operand, drop=_no_drop, site_p=0, site_out=0):
+    """q_in (B,Sq,d), kv_in (B,Sk,d); mask (Sq,Sk) additive or None.  drop(site, x2d): training-mode dropout hook
+    (oracle/dropout.py) on the attention probabilities (rows (b, h, query), cols key) and on the projected output."""
     B, Sq, d = q_in.shape
     Sk = kv_in.shape[1]
     hd = d // n_heads
@@ -63,15 +68,17 @@ def mha(q_in, kv_in, sd, prefix, n_heads, mask, operand):
     if mask is not None:
         s = s + mask
     p = torch.softmax(s, dim=-1)
+    p = drop(site_p, p.reshape(B * n_heads * Sq, Sk)).view(B, n_heads, Sq, Sk)
     o = torch.einsum("bhqk,bkhe->bqhe", p, v).reshape(B * Sq, d)
-    o = gemm(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"], operand)
+    o = drop(site_out, gemm(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"], operand))
     return o.view(B, Sq, d)
 
 
-def ffn(x, sd, prefix, operand):
+def ffn(x, sd, prefix, operand, drop=_no_drop, site_h=0, site_out=0):
     B, S, d = x.shape
     h = torch.relu(gemm(x.reshape(-1, d), sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"], operand))
-    return gemm(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"], operand).view(B, S, d)
+    h = drop(site_h, h)
+    return drop(site_out, gemm(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"], operand)).view(B, S, d)
 
 
 def count_layers(sd, which):
@@ -81,23 +88,30 @@ def count_layers(sd, which):
     return n
 
 
-def embed(x, sd, pe_index, operand):
-    """emb(x)[b,s] = (x[b,s] W^T + bias) * sqrt(d) + PE[pe_index[b]]   (models/transformer.py:53-56)."""
+def embed(x, sd, pe_index, operand, drop=_no_drop, site=0):
+    """emb(x)[b,s] = (x[b,s] W^T + bias) * sqrt(d) + PE[pe_index[b]]   (models/transformer.py:53-56), then the
+    dropout of positional_encoding.py:35."""
     B, S, E = x.shape
     W = sd["embedding.weight"]
     d = W.shape[0]
     e = gemm(x.reshape(-1, E), W, sd["embedding.bias"], operand).view(B, S, d) * math.sqrt(d)
     pe = sd["positional_encoder.pos_encoding"][:, 0, :].to(x.dtype)
-    return e + pe[pe_index][:, None, :]
+    return drop(site, (e + pe[pe_index][:, None, :]).reshape(B * S, d)).view(B, S, d)
 
 
-def forward(sd, src, tgt, n_heads, tgt_mask=None, pe_index=None, operand="fp32", hp_first=False):
+def forward(sd, src, tgt, n_heads, tgt_mask=None, pe_index=None, operand="fp32", hp_first=False, drop=None):
     """Returns (S_tgt, B, E) like models/transformer.py:65-68.
 
     ``pe_index`` (B,) long: PE row per clip; default arange(B) = the reference.
     ``hp_first``: keep the embedding and layer-0 Q/K/V projections in fp16x2 even
     when ``operand`` is a 16-bit format (the library's "mixed" mode).
+    ``drop``: None (eval mode) or an oracle.dropout.Dropper - training-mode dropout at nn.Transformer's sites.
     """
+    from . import dropout as D
+    if drop is None:
+        drop = _no_drop
+    elif hp_first and operand in ("fp16", "bf16"):
+        raise ValueError("dropout hooks are restated for the plain operand path only")
     B = src.shape[0]
     if pe_index is None:
         if B > 64:
@@ -106,9 +120,9 @@ def forward(sd, src, tgt, n_heads, tgt_mask=None, pe_index=None, operand="fp32",
     Le, Ld = count_layers(sd, "encoder"), count_layers(sd, "decoder")
     op0 = "fp16x2" if (hp_first and operand in ("fp16", "bf16")) else operand
 
-    def mha_l(q_in, kv_in, prefix, mask, first):
+    def mha_l(q_in, kv_in, prefix, mask, first, site_p=0, site_out=0):
         if not first or op0 == operand:
-            return mha(q_in, kv_in, sd, prefix, n_heads, mask, operand)
+            return mha(q_in, kv_in, sd, prefix, n_heads, mask, operand, drop, site_p, site_out)
         # layer-0 self-attention: QKV in high precision, out-proj in `operand`
         Bq, Sq, d = q_in.shape
         hd = d // n_heads
@@ -120,20 +134,25 @@ def forward(sd, src, tgt, n_heads, tgt_mask=None, pe_index=None, operand="fp32",
         o = torch.einsum("bhqk,bkhe->bqhe", torch.softmax(s, -1), qkv[:, :, 2]).reshape(Bq * Sq, d)
         return gemm(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"], operand).view(Bq, Sq, d)
 
-    x = embed(src, sd, pe_index, op0)
+    x = embed(src, sd, pe_index, op0, drop, 0)
     for l in range(Le):
         p = f"transformer.encoder.layers.{l}."
-        x = layer_norm(x + mha_l(x, x, p + "self_attn.", None, l == 0), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-        x = layer_norm(x + ffn(x, sd, p, operand), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+        x = layer_norm(x + mha_l(x, x, p + "self_attn.", None, l == 0, D.enc_site(l, D.SA_P), D.enc_site(l, D.SA_OUT)),
+                       sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        x = layer_norm(x + ffn(x, sd, p, operand, drop, D.enc_site(l, D.FF_H), D.enc_site(l, D.FF_OUT)),
+                       sd[p + "norm2.weight"], sd[p + "norm2.bias"])
     mem = layer_norm(x, sd["transformer.encoder.norm.weight"], sd["transformer.encoder.norm.bias"])
 
-    y = embed(tgt, sd, pe_index, op0)
+    y = embed(tgt, sd, pe_index, op0, drop, 1)
     for l in range(Ld):
         p = f"transformer.decoder.layers.{l}."
-        y = layer_norm(y + mha_l(y, y, p + "self_attn.", tgt_mask, l == 0), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-        y = layer_norm(y + mha(y, mem, sd, p + "multihead_attn.", n_heads, None, operand),
+        y = layer_norm(y + mha_l(y, y, p + "self_attn.", tgt_mask, l == 0, D.dec_site(l, D.SA_P), D.dec_site(l, D.SA_OUT)),
+                       sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        y = layer_norm(y + mha(y, mem, sd, p + "multihead_attn.", n_heads, None, operand, drop, D.dec_site(l, D.CA_P),
+                               D.dec_site(l, D.CA_OUT)),
                        sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-        y = layer_norm(y + ffn(y, sd, p, operand), sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+        y = layer_norm(y + ffn(y, sd, p, operand, drop, D.dec_site(l, D.FF_H), D.dec_site(l, D.FF_OUT)),
+                       sd[p + "norm3.weight"], sd[p + "norm3.bias"])
     y = layer_norm(y, sd["transformer.decoder.norm.weight"], sd["transformer.decoder.norm.bias"])
     Bt, St, d = y.shape
     out = gemm(y.reshape(-1, d), sd["out.weight"], sd["out.bias"], operand).view(Bt, St, -1)

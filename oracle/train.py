@@ -38,3 +38,21 @@ def make_batch(B, S, E, seed, sos=True):
     if sos:
         x[:, 0] = 2.0
     return x
+
+
+def train_grads_functional(state_dict, n_heads, new_batch, frames_to_predict, pe_index=None, drop=None, **loss_kw):
+    """Same iteration on the op-by-op restatement (oracle/functional.py) under autograd - used where hooks are needed:
+    ``pe_index`` (data-parallel shards) and ``drop`` (an oracle.dropout.Dropper: training-mode dropout with the
+    library's own masks, DROPOUT_P of the reference's configs).  Returns (loss, pred, {name: grad}) for the float
+    parameters of ``state_dict`` (the positional table is a buffer and gets no gradient)."""
+    from . import functional as F
+    sd = {k: v.detach().clone() for k, v in state_dict.items()}
+    names = [k for k in sd if k != "positional_encoder.pos_encoding"]
+    for k in names:
+        sd[k].requires_grad_(True)
+    y_input = new_batch[:, :-1]
+    y_expected = new_batch[:, 1:].permute(1, 0, 2)
+    pred = F.forward(sd, new_batch, y_input, n_heads, F.causal_mask(y_input.size(1), new_batch.dtype), pe_index=pe_index, drop=drop)
+    loss = losses.criterion(**loss_kw)(pred[-frames_to_predict:], y_expected[-frames_to_predict:])
+    loss.backward()
+    return loss.detach(), pred.detach(), {k: sd[k].grad.detach().clone() for k in names}

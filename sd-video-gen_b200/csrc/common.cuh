@@ -53,7 +53,25 @@ struct Epilogue {
   const float* alpha_dev = nullptr;
   const float* gate = nullptr;
   int ld_gate = 0;
+  float gate_scale = 1.0f;   // kept values are multiplied by this (1 / (1 - p) when the gate also carries a dropout mask)
+  // training-mode dropout (after ReLU, before the residual): element (row, col) is kept iff
+  // drop_hash(drop_key, row * drop_cols + col) >= drop_thr, and then multiplied by drop_scale = 1 / (1 - p)
+  uint32_t drop_thr = 0;
+  uint32_t drop_key = 0;
+  int drop_cols = 0;
+  float drop_scale = 1.0f;
 };
+
+// Counter-based dropout mask (murmur3 finaliser of a per-site key and the element index): the same mask is
+// regenerated in the backward pass, and the CPU checker of the test-suite restates it bit for bit for the parity tests.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t key, uint32_t idx) { return fmix32(idx * 0x9E3779B1u + key); }
+__host__ __device__ __forceinline__ uint32_t drop_site_key(uint64_t seed, uint32_t step, uint32_t site) {
+  return fmix32(static_cast<uint32_t>(seed) ^ fmix32(site * 0x632BE5ABu + step)) ^ static_cast<uint32_t>(seed >> 32);
+}
 
 __device__ __forceinline__ int epi_out_row(const Epilogue& e, int row) {
   if (e.row_map == 0) return row;
@@ -81,9 +99,12 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, float acc, int row
   if (e.bias) v += __ldg(e.bias + col);
   v *= e.alpha;
   if (e.alpha_dev) v *= __ldg(e.alpha_dev);
-  if (e.gate && __ldg(e.gate + static_cast<size_t>(row) * e.ld_gate + col) <= 0.0f) v = 0.0f;
+  if (e.gate) v = __ldg(e.gate + static_cast<size_t>(row) * e.ld_gate + col) > 0.0f ? v * e.gate_scale : 0.0f;
   if (pe_row >= 0) v += __ldg(e.pe + static_cast<size_t>(pe_row) * e.ld_pe + col);
   if (e.relu) v = fmaxf(v, 0.0f);
+  if (e.drop_thr)
+    v = drop_hash(e.drop_key, static_cast<uint32_t>(row) * static_cast<uint32_t>(e.drop_cols) + static_cast<uint32_t>(col)) >= e.drop_thr
+            ? v * e.drop_scale : 0.0f;
   if (e.residual) {
     const int rrow = epi_res_row(e, row);
     float r = __ldg(e.residual + static_cast<size_t>(rrow) * e.ld_res + col);

@@ -318,7 +318,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
             v.x *= al; v.y *= al; v.z *= al; v.w *= al;
             if (e.gate) {
               const float4 gt = __ldg(reinterpret_cast<const float4*>(e.gate + static_cast<size_t>(row) * e.ld_gate + col));
-              v.x = gt.x > 0.f ? v.x : 0.f; v.y = gt.y > 0.f ? v.y : 0.f; v.z = gt.z > 0.f ? v.z : 0.f; v.w = gt.w > 0.f ? v.w : 0.f;
+              const float gs = e.gate_scale;
+              v.x = gt.x > 0.f ? v.x * gs : 0.f; v.y = gt.y > 0.f ? v.y * gs : 0.f;
+              v.z = gt.z > 0.f ? v.z * gs : 0.f; v.w = gt.w > 0.f ? v.w * gs : 0.f;
             }
             if (e.pe || e.row_map) {
               const int b = row / e.rows_per_clip, sidx = row - b * e.rows_per_clip;
@@ -333,6 +335,16 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
             }
           }
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if constexpr (FANCY) {
+            if (e.drop_thr) {   // training-mode dropout, mask regenerated from (row, col) in the backward pass
+              const uint32_t i0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(e.drop_cols) + static_cast<uint32_t>(col);
+              const float ds = e.drop_scale;
+              v.x = drop_hash(e.drop_key, i0) >= e.drop_thr ? v.x * ds : 0.f;
+              v.y = drop_hash(e.drop_key, i0 + 1) >= e.drop_thr ? v.y * ds : 0.f;
+              v.z = drop_hash(e.drop_key, i0 + 2) >= e.drop_thr ? v.z * ds : 0.f;
+              v.w = drop_hash(e.drop_key, i0 + 3) >= e.drop_thr ? v.w * ds : 0.f;
+            }
+          }
           if (residual) {
             float4 rv = pre.res[j % PF][i];
             if (ln_res) {  // LayerNorm of the pre-norm sums, recomputed from the row statistics
@@ -363,7 +375,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
 // The embedding / output projections are the only GEMMs that scale, add positional rows or remap output rows.
 inline bool epilogue_is_fancy(const Epilogue& e) {
   return e.alpha != 1.0f || e.pe != nullptr || e.row_map != 0 || e.res_clip_rows != 0 || e.alpha_dev != nullptr ||
-         e.gate != nullptr;
+         e.gate != nullptr || e.drop_thr != 0;
 }
 
 template <int BN, bool SPLIT, bool FANCY>

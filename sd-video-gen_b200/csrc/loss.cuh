@@ -123,12 +123,21 @@ struct LossFinalArgs {
 __global__ void loss_finalize_kernel(const __grid_constant__ LossFinalArgs a) {
   pdl_wait();
   pdl_trigger();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  // one warp: fixed strided order + shuffle tree (deterministic), instead of one thread walking ~2000 partials
+  const int lane = threadIdx.x;
   double s[3] = {0.0, 0.0, 0.0};
-  for (int b = 0; b < a.n_blocks; ++b)
+  for (int b = lane; b < a.n_blocks; b += 32)
     for (int k = 0; k < 3; ++k) s[k] += a.partial[b * 4 + k];
   double n1 = 0.0, n2 = 0.0;
-  for (int b = 0; b < a.n_ct; ++b) { n1 += a.nce_partial[b * 2]; n2 += a.nce_partial[b * 2 + 1]; }
+  for (int b = lane; b < a.n_ct; b += 32) { n1 += a.nce_partial[b * 2]; n2 += a.nce_partial[b * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int k = 0; k < 3; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  if (lane != 0) return;
   const double mse = s[0] / a.numel, l1 = s[1] / a.numel, gdl = s[2] / a.numel;
   const double nce = a.n_ct ? 0.5 * (n1 + n2) / a.nce_rows : 0.0;
   const double total = a.use_mse * mse + a.use_l1 * l1 + a.use_gdl * a.lambda_gdl * gdl + a.use_nce * a.lambda_nce * nce;

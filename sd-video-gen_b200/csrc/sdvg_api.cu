@@ -152,6 +152,15 @@ int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t*
   return SDVG_OK;
 }
 
+int sdvg_train_set_dropout(sdvg_handle* h, float p, uint64_t seed) {
+  if (!h) return SDVG_ERR_INVALID;
+  if (!(p >= 0.f) || p >= 1.f) return h->eng.fail(SDVG_ERR_INVALID, "dropout probability must be in [0, 1)");
+  sdvg::Trainer* t = trainer_of(h);
+  if (!t) return h->eng.fail(SDVG_ERR_INVALID, "out of host memory");
+  t->drop_p = p; t->drop_seed = seed;
+  return SDVG_OK;
+}
+
 int sdvg_train_set_ready_callback(sdvg_handle* h, sdvg_grad_ready_fn fn, void* user, int32_t layers_per_bucket) {
   if (!h) return SDVG_ERR_INVALID;
   sdvg::Trainer* t = trainer_of(h);

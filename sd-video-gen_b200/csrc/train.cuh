@@ -30,6 +30,7 @@ struct PackTArgs {
   float* colsum; const float* colsum_mul_dev; int colsum_accumulate;   // colsum[c] (+)= (*colsum_mul_dev) * sum_r v[r][c]  (nullable)
   int bf16;
   int rows_per_block;                  // rows one CTA walks through (a multiple of 128)
+  uint32_t drop_thr, drop_key; float drop_scale;   // drop_thr != 0: v *= dropout mask of element (r, c) (index r * C + c)
 };
 
 __global__ void __launch_bounds__(256) pack_t_kernel(const __grid_constant__ PackTArgs a) {
@@ -60,7 +61,10 @@ __global__ void __launch_bounds__(256) pack_t_kernel(const __grid_constant__ Pac
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int rl = warp + 8 * i, r = r0 + rl;
-      const float x = v[i] * mul;
+      float x = v[i] * mul;
+      if (a.drop_thr)
+        x = drop_hash(a.drop_key, static_cast<uint32_t>(r) * static_cast<uint32_t>(a.C) + static_cast<uint32_t>(c)) >= a.drop_thr
+                ? x * a.drop_scale : 0.f;
       if (a.out_hi && r < a.R && c < a.C) {
         const uint16_t h = to_plane_hi(x, a.bf16);
         a.out_hi[static_cast<size_t>(r) * a.ld16 + c] = h;
@@ -195,8 +199,13 @@ struct AttnBwdArgs {
   float* dq; int ld_dq; float* dk; float* dv; int ld_dkv;
   int clips, heads, hd, Sq, Sk, causal;
   float scale;
+  int cshift;   // hd == 32 << cshift, or -1
+  uint32_t drop_thr, drop_key; float drop_scale;   // dropout on the attention probabilities: index ((b H + h) Sq + i) Sk + j
 };
 
+// SMAX bounds both sequence lengths at compile time (6 covers the reference's 5 / 6 token windows) so that the
+// score / output loops unroll and their shared-memory loads are issued in batches instead of one per FMA.
+template <int SMAX>
 __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_constant__ AttnBwdArgs a) {
   extern __shared__ float attn_bwd_smem[];   // per warp: Q[Sq][hd+1], dO[Sq][hd+1], K[Sk][hd+1], V[Sk][hd+1]
   __shared__ float sP[4][kTrainMaxS][kTrainMaxS];
@@ -218,22 +227,42 @@ __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_co
   float* sV = sK + Sk * ldp;
   float (*P)[kTrainMaxS] = sP[wib];
   float (*D)[kTrainMaxS] = sD[wib];
-  // stage the four operands (all loads in flight together; rows are contiguous hd floats)
-  for (int i = 0; i < Sq; ++i)
-    for (int e = lane; e < hd; e += 32) {
-      sQ[i * ldp + e] = __ldg(q + static_cast<size_t>(i) * a.ldq + e);
-      sO[i * ldp + e] = __ldg(dO + static_cast<size_t>(i) * a.ld_do + e);
+  // stage the four operands (smem rows are laid out Q, dO, K, V).  hd = 32 << cshift: 32-element chunks, eight
+  // independent loads in flight per lane (16 per batch), shifts instead of divisions; other head sizes take the plain loop
+  {
+    const int nrows = 2 * Sq + 2 * Sk;
+    auto row_ptr = [&](int r) -> const float* {
+      return r < Sq ? q + static_cast<size_t>(r) * a.ldq
+           : r < 2 * Sq ? dO + static_cast<size_t>(r - Sq) * a.ld_do
+           : r < 2 * Sq + Sk ? k + static_cast<size_t>(r - 2 * Sq) * a.ldkv
+                             : v + static_cast<size_t>(r - 2 * Sq - Sk) * a.ldkv;
+    };
+    if (a.cshift >= 0) {
+      const int nchunks = nrows << a.cshift, cmask = (1 << a.cshift) - 1;
+      for (int c0 = 0; c0 < nchunks; c0 += 16) {
+        float tmp[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int ci = c0 + u;
+          tmp[u] = ci < nchunks ? __ldg(row_ptr(ci >> a.cshift) + ((ci & cmask) << 5) + lane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int ci = c0 + u;
+          if (ci < nchunks) sQ[(ci >> a.cshift) * ldp + ((ci & cmask) << 5) + lane] = tmp[u];
+        }
+      }
+    } else {
+      for (int r = 0; r < nrows; ++r)
+        for (int e = lane; e < hd; e += 32) sQ[r * ldp + e] = __ldg(row_ptr(r) + e);
     }
-  for (int j = 0; j < Sk; ++j)
-    for (int e = lane; e < hd; e += 32) {
-      sK[j * ldp + e] = __ldg(k + static_cast<size_t>(j) * a.ldkv + e);
-      sV[j * ldp + e] = __ldg(v + static_cast<size_t>(j) * a.ldkv + e);
-    }
+  }
   __syncwarp();
   // scores and dP: one (query, key) pair per lane (row pitch hd+1: conflict-free)
   for (int p = lane; p < Sq * Sk; p += 32) {
     const int i = p / Sk, j = p - i * Sk;
     float s = 0.f, dp = 0.f;
+#pragma unroll 8
     for (int e = 0; e < hd; ++e) {
       s = fmaf(sQ[i * ldp + e], sK[j * ldp + e], s);
       dp = fmaf(sO[i * ldp + e], sV[j * ldp + e], dp);
@@ -251,29 +280,52 @@ __global__ void __launch_bounds__(128) attention_backward_kernel(const __grid_co
     for (int j = 0; j < Sk; ++j) { const float p = __expf(P[i][j] - mx); P[i][j] = p; sum += p; }
     const float inv = 1.0f / sum;
     float dot = 0.f;
-    for (int j = 0; j < Sk; ++j) { P[i][j] *= inv; dot = fmaf(P[i][j], D[i][j], dot); }
-    for (int j = 0; j < Sk; ++j) D[i][j] = P[i][j] * (D[i][j] - dot);   // dS
+    const uint32_t drow = static_cast<uint32_t>((b * a.heads + h) * Sq + i) * static_cast<uint32_t>(Sk);
+    for (int j = 0; j < Sk; ++j) {
+      P[i][j] *= inv;
+      if (a.drop_thr) D[i][j] = drop_hash(a.drop_key, drow + j) >= a.drop_thr ? D[i][j] * a.drop_scale : 0.f;   // dP = dP_d o mask / (1-p)
+      dot = fmaf(P[i][j], D[i][j], dot);
+    }
+    for (int j = 0; j < Sk; ++j) {
+      D[i][j] = P[i][j] * (D[i][j] - dot);   // dS
+      if (a.drop_thr) P[i][j] = drop_hash(a.drop_key, drow + j) >= a.drop_thr ? P[i][j] * a.drop_scale : 0.f;   // P_d, for dV
+    }
   }
   __syncwarp();
   for (int e = lane; e < hd; e += 32) {
-    for (int i = 0; i < Sq; ++i) {
-      float acc = 0.f;
-      for (int j = 0; j < Sk; ++j) acc = fmaf(D[i][j], sK[j * ldp + e], acc);
-      a.dq[(static_cast<size_t>(b) * Sq + i) * a.ld_dq + h * hd + e] = acc * a.scale;
-    }
-    for (int j = 0; j < Sk; ++j) {
-      float ak = 0.f, av = 0.f;
-      for (int i = 0; i < Sq; ++i) {
-        ak = fmaf(D[i][j], sQ[i * ldp + e], ak);
-        av = fmaf(P[i][j], sO[i * ldp + e], av);
+    float kk[SMAX], qq[SMAX], oo[SMAX];
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) kk[j] = j < Sk ? sK[j * ldp + e] : 0.f;
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) { qq[i] = i < Sq ? sQ[i * ldp + e] : 0.f; oo[i] = i < Sq ? sO[i * ldp + e] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) {
+      if (i < Sq) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) if (j < Sk) acc = fmaf(D[i][j], kk[j], acc);
+        a.dq[(static_cast<size_t>(b) * Sq + i) * a.ld_dq + h * hd + e] = acc * a.scale;
       }
-      a.dk[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = ak * a.scale;
-      a.dv[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = av;
+    }
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+      if (j < Sk) {
+        float ak = 0.f, av = 0.f;
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+          if (i < Sq) { ak = fmaf(D[i][j], qq[i], ak); av = fmaf(P[i][j], oo[i], av); }
+        }
+        a.dk[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = ak * a.scale;
+        a.dv[(static_cast<size_t>(b) * Sk + j) * a.ld_dkv + h * hd + e] = av;
+      }
     }
   }
 }
 
-inline cudaError_t launch_attention_backward(const AttnBwdArgs& a, cudaStream_t stream) {
+inline cudaError_t launch_attention_backward(const AttnBwdArgs& a_in, cudaStream_t stream) {
+  AttnBwdArgs a = a_in;
+  a.cshift = -1;
+  for (int sft = 0; sft < 4; ++sft) if (a.hd == (32 << sft)) a.cshift = sft;
   if (a.Sq > kTrainMaxS || a.Sk > kTrainMaxS) return cudaErrorInvalidValue;
   const size_t smem = 4 * static_cast<size_t>(2 * a.Sq + 2 * a.Sk) * (a.hd + 1) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -282,12 +334,107 @@ inline cudaError_t launch_attention_backward(const AttnBwdArgs& a, cudaStream_t 
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-      cudaError_t e = cudaFuncSetAttribute(attention_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(attention_backward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_backward_kernel<kTrainMaxS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return e;
       attr_set[dev & 63] = true;
     }
   }
-  return launch_kernel(attention_backward_kernel, dim3(ceil_div(a.clips * a.heads, 4)), dim3(128), smem, stream, a);
+  const dim3 grid(ceil_div(a.clips * a.heads, 4));
+  if (a.Sq <= 6 && a.Sk <= 6) return launch_kernel(attention_backward_kernel<6>, grid, dim3(128), smem, stream, a);
+  return launch_kernel(attention_backward_kernel<kTrainMaxS>, grid, dim3(128), smem, stream, a);
+}
+
+// ------------------------------------------------------------------------------------------------ attention forward (dropout)
+// Training-mode attention with dropout on the probabilities (torch.nn.MultiheadAttention(dropout=p), as constructed
+// by nn.Transformer at models/transformer.py:38-44).  Same staging as the backward kernel; used only when p > 0 -
+// without dropout the training forward uses the inference attention kernels.
+struct AttnTrainArgs {
+  const float* q; int ldq; const float* k; const float* v; int ldkv;
+  int clips, heads, hd, Sq, Sk, causal;
+  float scale;
+  float* out32; int ld32;
+  uint16_t* out_hi; uint16_t* out_lo; int ld16; int bf16;
+  uint32_t drop_thr, drop_key; float drop_scale;
+};
+
+__global__ void __launch_bounds__(128) attention_train_fwd_kernel(const __grid_constant__ AttnTrainArgs a) {
+  extern __shared__ float attn_fwd_smem[];   // per warp: Q[Sq][hd+1], K[Sk][hd+1], V[Sk][hd+1]
+  __shared__ float sP[4][kTrainMaxS][kTrainMaxS];
+  pdl_wait();
+  pdl_trigger();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + wib;
+  if (wg >= a.clips * a.heads) return;
+  const int b = wg / a.heads, h = wg - b * a.heads;
+  const int hd = a.hd, Sq = a.Sq, Sk = a.Sk, ldp = hd + 1;
+  const float* q = a.q + static_cast<size_t>(b) * Sq * a.ldq + h * hd;
+  const float* k = a.k + static_cast<size_t>(b) * Sk * a.ldkv + h * hd;
+  const float* v = a.v + static_cast<size_t>(b) * Sk * a.ldkv + h * hd;
+  float* sQ = attn_fwd_smem + static_cast<size_t>(wib) * (Sq + 2 * Sk) * ldp;
+  float* sK = sQ + Sq * ldp;
+  float* sV = sK + Sk * ldp;
+  float (*P)[kTrainMaxS] = sP[wib];
+  for (int r = 0; r < Sq + 2 * Sk; ++r) {
+    const float* src = r < Sq ? q + static_cast<size_t>(r) * a.ldq : r < Sq + Sk ? k + static_cast<size_t>(r - Sq) * a.ldkv
+                                                                                 : v + static_cast<size_t>(r - Sq - Sk) * a.ldkv;
+    for (int e = lane; e < hd; e += 32) sQ[r * ldp + e] = __ldg(src + e);
+  }
+  __syncwarp();
+  for (int p = lane; p < Sq * Sk; p += 32) {
+    const int i = p / Sk, j = p - i * Sk;
+    float s = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < hd; ++e) s = fmaf(sQ[i * ldp + e], sK[j * ldp + e], s);
+    P[i][j] = (a.causal && j > i + (Sk - Sq)) ? -INFINITY : s * a.scale;
+  }
+  __syncwarp();
+  if (lane < Sq) {
+    const int i = lane;
+    float mx = -INFINITY;
+    for (int j = 0; j < Sk; ++j) mx = fmaxf(mx, P[i][j]);
+    float sum = 0.f;
+    for (int j = 0; j < Sk; ++j) { const float pv = __expf(P[i][j] - mx); P[i][j] = pv; sum += pv; }
+    const float inv = 1.0f / sum;
+    const uint32_t drow = static_cast<uint32_t>((b * a.heads + h) * Sq + i) * static_cast<uint32_t>(Sk);
+    for (int j = 0; j < Sk; ++j) {
+      float pv = P[i][j] * inv;
+      if (a.drop_thr) pv = drop_hash(a.drop_key, drow + j) >= a.drop_thr ? pv * a.drop_scale : 0.f;
+      P[i][j] = pv;
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < hd; e += 32) {
+    for (int i = 0; i < Sq; ++i) {
+      float acc = 0.f;
+      for (int j = 0; j < Sk; ++j) acc = fmaf(P[i][j], sV[j * ldp + e], acc);
+      const size_t row = static_cast<size_t>(b) * Sq + i;
+      const int col = h * hd + e;
+      if (a.out32) a.out32[row * a.ld32 + col] = acc;
+      if (a.out_hi) {
+        const uint16_t hi = to_plane_hi(acc, a.bf16);
+        a.out_hi[row * a.ld16 + col] = hi;
+        if (a.out_lo) a.out_lo[row * a.ld16 + col] = to_plane_lo(acc, hi);
+      }
+    }
+  }
+}
+
+inline cudaError_t launch_attention_train_fwd(const AttnTrainArgs& a, cudaStream_t stream) {
+  if (a.Sq > kTrainMaxS || a.Sk > kTrainMaxS) return cudaErrorInvalidValue;
+  const size_t smem = 4 * static_cast<size_t>(a.Sq + 2 * a.Sk) * (a.hd + 1) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 40 * 1024) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(attention_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set[dev & 63] = true;
+    }
+  }
+  return launch_kernel(attention_train_fwd_kernel, dim3(ceil_div(a.clips * a.heads, 4)), dim3(128), smem, stream, a);
 }
 
 // ------------------------------------------------------------------------------------------------ criterion gradient

@@ -26,6 +26,9 @@ struct TrainLoss {
   float temperature, lambda_nce;
 };
 
+// dropout mask of one site: element kept iff drop_hash(key, index) >= thr, then multiplied by scale (thr == 0: off)
+struct Drop { uint32_t thr = 0, key = 0; float scale = 1.f; };
+
 class Trainer {
  public:
   Engine& g;
@@ -109,6 +112,30 @@ class Trainer {
     return cudaSuccess;
   }
   size_t offset_of(const float* p) const { return static_cast<size_t>(p - g.arena); }
+
+  // Training-mode dropout (DROPOUT_P of the reference's configs; nn.Transformer applies it to the embedding + PE sum,
+  // the attention probabilities, every sub-layer output before its residual add and the FFN hidden activation).
+  // Masks come from a counter-based hash of (seed, step, site, element) - common.cuh drop_hash - so the backward pass
+  // regenerates them instead of storing them; torch's own Philox stream is not reproduced (include/sdvg.h).
+  float drop_p = 0.f;
+  uint64_t drop_seed = 0;
+  uint32_t drop_step = 0;
+  enum Site { SA_P = 0, SA_OUT = 1, CA_P = 2, CA_OUT = 3, FF_H = 4, FF_OUT = 5 };
+  Drop drop_at(uint32_t site) const {
+    Drop dr;
+    if (drop_p <= 0.f) return dr;
+    double t = static_cast<double>(drop_p) * 4294967296.0;
+    dr.thr = t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+    if (dr.thr == 0) dr.thr = 1;
+    dr.key = drop_site_key(drop_seed, drop_step, site);
+    dr.scale = 1.0f / (1.0f - drop_p);
+    return dr;
+  }
+  static uint32_t enc_site(int l, int which) { return 1000u + static_cast<uint32_t>(l) * 10u + which; }
+  static uint32_t dec_site(int l, int which) { return 2000u + static_cast<uint32_t>(l) * 10u + which; }
+  static void set_drop(Epilogue& e, const Drop& dr, int cols) {
+    e.drop_thr = dr.thr; e.drop_key = dr.key; e.drop_scale = dr.scale; e.drop_cols = cols;
+  }
 
   // ------------------------------------------------------------------ set-up
   int slot_containing(const float* p) const {
@@ -257,7 +284,18 @@ class Trainer {
   ActBuf act(float* f32, int ld, const Planes& p) const { ActBuf a; a.f32 = f32; a.ld32 = ld; a.p = p; return a; }
 
   cudaError_t attention_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, int B, int Sq, int Sk, int causal,
-                            float* out32, cudaStream_t st) {
+                            float* out32, cudaStream_t st, const Drop& dr = Drop{}) {
+    if (dr.thr) {
+      AttnTrainArgs t{};
+      t.q = q; t.ldq = ldq; t.k = k; t.v = v; t.ldkv = ldkv;
+      t.clips = B; t.heads = g.cfg.num_heads; t.hd = g.cfg.dim_model / g.cfg.num_heads; t.Sq = Sq; t.Sk = Sk; t.causal = causal;
+      t.scale = 1.0f / sqrtf(static_cast<float>(t.hd));
+      t.out32 = out32; t.ld32 = g.cfg.dim_model;
+      t.out_hi = g.attn.p.hi; t.out_lo = g.attn.p.lo; t.ld16 = g.attn.p.ld; t.bf16 = g.bf16();
+      t.drop_thr = dr.thr; t.drop_key = dr.key; t.drop_scale = dr.scale;
+      Engine::Scope sc(&g, KC_ATTN, 0.0, 4.0 * B * g.cfg.dim_model * (2.0 * Sq + 2.0 * Sk), st);
+      return launch_attention_train_fwd(t, st);
+    }
     AttnArgs a{};
     a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv;
     a.clips = B; a.heads = g.cfg.num_heads; a.hd = g.cfg.dim_model / g.cfg.num_heads; a.Sq = Sq; a.Sk = Sk;
@@ -286,8 +324,10 @@ class Trainer {
   }
 
   cudaError_t attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* dO, float* dq, int ld_dq,
-                            float* dk, float* dv, int ld_dkv, int B, int Sq, int Sk, int causal, cudaStream_t st) {
+                            float* dk, float* dv, int ld_dkv, int B, int Sq, int Sk, int causal, cudaStream_t st,
+                            const Drop& dr = Drop{}) {
     AttnBwdArgs a{};
+    a.drop_thr = dr.thr; a.drop_key = dr.key; a.drop_scale = dr.scale;
     a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldkv = ldkv; a.dO = dO; a.ld_do = g.cfg.dim_model;
     a.dq = dq; a.ld_dq = ld_dq; a.dk = dk; a.dv = dv; a.ld_dkv = ld_dkv;
     a.clips = B; a.heads = g.cfg.num_heads; a.hd = g.cfg.dim_model / g.cfg.num_heads; a.Sq = Sq; a.Sk = Sk; a.causal = causal;
@@ -298,8 +338,10 @@ class Trainer {
 
   // dY fp32 [M][N] -> operand planes, transposed operand planes, bias gradient
   cudaError_t pack_dy(const float* dy, int ld, int M, int N, float* gb, bool accumulate_b, cudaStream_t st, float mul = 1.0f,
-                      const float* mul_dev = nullptr, int perm_S = 0, int perm_B = 0, bool want_planes = true) {
+                      const float* mul_dev = nullptr, int perm_S = 0, int perm_B = 0, bool want_planes = true,
+                      const Drop& dr = Drop{}) {
     PackTArgs a{};
+    a.drop_thr = dr.thr; a.drop_key = dr.key; a.drop_scale = dr.scale;
     a.src = dy; a.ld_src = ld; a.R = M; a.C = N; a.perm_S = perm_S; a.perm_B = perm_B; a.mul = mul; a.mul_dev = mul_dev;
     if (want_planes) { const ActBuf& v = dA.at(N); a.out_hi = v.p.hi; a.out_lo = v.p.lo; a.ld16 = v.p.ld; }
     a.t_hi = dAT.p.hi; a.t_lo = dAT.p.lo; a.ld_t = dAT.p.ld; a.Rpad = round_up(M, kTcBK);
@@ -327,20 +369,24 @@ class Trainer {
     return g.gemm(dAT, L, N, e, st);
   }
   // dX[M][K] = dY W (+ residual), from the planes left by pack_dy
-  cudaError_t grad_x(const TLinear& tl, int M, float* dx, const float* residual, const float* gate, int ld_gate, cudaStream_t st) {
+  cudaError_t grad_x(const TLinear& tl, int M, float* dx, const float* residual, const float* gate, int ld_gate, cudaStream_t st,
+                     float gate_scale = 1.0f) {
     Epilogue e;
     e.out32 = dx; e.ld32 = tl.t.N;
     if (residual) { e.residual = residual; e.ld_res = tl.t.N; }
-    if (gate) { e.gate = gate; e.ld_gate = ld_gate; }
+    if (gate) { e.gate = gate; e.ld_gate = ld_gate; e.gate_scale = gate_scale; }
     return g.gemm(dA.at(tl.t.K), tl.t, M, e, st);
   }
   // full backward of one linear layer whose input x (fp32, saved) has M rows
+  // out_drop: dropout that the forward pass applied to this layer's OUTPUT (dy is masked the same way on the way in);
+  // gate / gate_scale: ReLU (+ dropout) that the forward pass applied to this layer's INPUT (masks dx)
   cudaError_t linear_bwd(const TLinear& tl, const float* dy, int ld_dy, const float* x, int M, float* dx, const float* residual,
-                         cudaStream_t st, const float* gate = nullptr, int ld_gate = 0, Linear* xt_ready = nullptr) {
+                         cudaStream_t st, const float* gate = nullptr, int ld_gate = 0, Linear* xt_ready = nullptr,
+                         const Drop& out_drop = Drop{}, float gate_scale = 1.0f) {
     SDVG_CK(weight_branch_begin(st));
-    SDVG_CK(pack_dy(dy, ld_dy, M, tl.fwd.N, tl.gb, false, st));
+    SDVG_CK(pack_dy(dy, ld_dy, M, tl.fwd.N, tl.gb, false, st, 1.0f, nullptr, 0, 0, true, out_drop));
     SDVG_CK(weight_branch(tl.fwd.N, tl.fwd.K, M, tl.gw, false, xt_ready ? nullptr : x, tl.fwd.K, xt_ready ? *xt_ready : XT, st));
-    if (dx) SDVG_CK(grad_x(tl, M, dx, residual, gate, ld_gate, st));
+    if (dx) SDVG_CK(grad_x(tl, M, dx, residual, gate, ld_gate, st, gate_scale));
     return cudaSuccess;
   }
   // before dAT is overwritten: the side stream must be done with the previous layer's dW GEMM
@@ -380,54 +426,63 @@ class Trainer {
     const int Le = static_cast<int>(g.enc.size()), Ld = static_cast<int>(g.dec.size());
     const float sqrt_d = sqrtf(static_cast<float>(d));
     Bc = B; Ssc = Ss; Stc = St; src_c = src; tgt_c = tgt;
+    ++drop_step;
     SDVG_CK(g.ingest(src, static_cast<long long>(Ss) * E, E, nullptr, B, Ss, 1.0f, g.lat_s, st));
     SDVG_CK(g.ingest(tgt, static_cast<long long>(St) * E, E, nullptr, B, St, 1.0f, g.lat_t, st));
-    auto embed = [&](const ActBuf& lat, int S, float* out32, const ActBuf& planes) -> cudaError_t {
-      Epilogue e;  // models/transformer.py:53-56
+    auto embed = [&](const ActBuf& lat, int S, float* out32, const ActBuf& planes, uint32_t site) -> cudaError_t {
+      Epilogue e;  // models/transformer.py:53-56, dropout of positional_encoding.py:35
       e.alpha = sqrt_d; e.pe = g.pe_table; e.ld_pe = d; e.pe_index = pe_index; e.rows_per_clip = S;
+      set_drop(e, drop_at(site), d);
       e.out32 = out32; e.ld32 = d; e.out_hi = planes.p.hi; e.out_lo = planes.p.lo; e.ld16 = planes.p.ld;
       return g.gemm(lat, g.embedding, B * S, e, st);
     };
     auto plain = [&](float* out32, int ld) { Epilogue e; e.out32 = out32; e.ld32 = ld; return e; };
     // ---- encoder
-    SDVG_CK(embed(g.lat_s, Ss, xe[0], g.emb_s));
+    SDVG_CK(embed(g.lat_s, Ss, xe[0], g.emb_s, 0));
     const ActBuf* x = &g.emb_s;
     for (int l = 0; l < Le; ++l) {
       const EncLayer& L = g.enc[l]; EncSave& s = se[l];
       SDVG_CK(g.gemm(*x, L.sa.qkv, Ms, plain(s.qkv, 3 * d), st));
-      SDVG_CK(attention_fwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, B, Ss, Ss, 0, s.a, st));
+      SDVG_CK(attention_fwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, B, Ss, Ss, 0, s.a, st, drop_at(enc_site(l, SA_P))));
       Epilogue eo = plain(s.y1, d); eo.residual = xe[l]; eo.ld_res = d;
+      set_drop(eo, drop_at(enc_site(l, SA_OUT)), d);
       SDVG_CK(g.gemm(g.attn, L.sa.out, Ms, eo, st));
       SDVG_CK(ln_fwd(s.y1, Ms, Ss, L.n1, s.x1, g.xs.p, s.st1, st));
       Epilogue e1 = plain(s.h, g.cfg.dim_feedforward); e1.relu = 1;
       e1.out_hi = g.ffh.p.hi; e1.out_lo = g.ffh.p.lo; e1.ld16 = g.ffh.p.ld;
+      set_drop(e1, drop_at(enc_site(l, FF_H)), g.cfg.dim_feedforward);
       SDVG_CK(g.gemm(g.xs, L.ff1, Ms, e1, st));
       Epilogue e2 = plain(s.y2, d); e2.residual = s.x1; e2.ld_res = d;
+      set_drop(e2, drop_at(enc_site(l, FF_OUT)), d);
       SDVG_CK(g.gemm(g.ffh, L.ff2, Ms, e2, st));
       SDVG_CK(ln_fwd(s.y2, Ms, Ss, L.n2, xe[l + 1], g.xs.p, s.st2, st));
       x = &g.xs;
     }
     SDVG_CK(ln_fwd(xe[Le], Ms, Ss, g.enc_norm, mem32, g.mem.p, st_enc, st));
     // ---- decoder
-    SDVG_CK(embed(g.lat_t, St, xd[0], g.emb_t));
+    SDVG_CK(embed(g.lat_t, St, xd[0], g.emb_t, 1));
     const ActBuf* y = &g.emb_t;
     for (int l = 0; l < Ld; ++l) {
       const DecLayer& L = g.dec[l]; DecSave& s = sd[l];
       SDVG_CK(g.gemm(*y, L.sa.qkv, Mt, plain(s.qkv, 3 * d), st));
-      SDVG_CK(attention_fwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, B, St, St, 1, s.a, st));
+      SDVG_CK(attention_fwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, B, St, St, 1, s.a, st, drop_at(dec_site(l, SA_P))));
       Epilogue eo = plain(s.y1, d); eo.residual = xd[l]; eo.ld_res = d;
+      set_drop(eo, drop_at(dec_site(l, SA_OUT)), d);
       SDVG_CK(g.gemm(g.attn, L.sa.out, Mt, eo, st));
       SDVG_CK(ln_fwd(s.y1, Mt, St, L.n1, s.x1, g.xt.p, s.st1, st));
       SDVG_CK(g.gemm(g.xt, L.ca.q, Mt, plain(s.qc, d), st));
       SDVG_CK(g.gemm(g.mem, L.ca.kv, Ms, plain(s.kvc, 2 * d), st));
-      SDVG_CK(attention_fwd(s.qc, d, s.kvc, s.kvc + d, 2 * d, B, St, Ss, 0, s.ac, st));
+      SDVG_CK(attention_fwd(s.qc, d, s.kvc, s.kvc + d, 2 * d, B, St, Ss, 0, s.ac, st, drop_at(dec_site(l, CA_P))));
       Epilogue eo2 = plain(s.y2, d); eo2.residual = s.x1; eo2.ld_res = d;
+      set_drop(eo2, drop_at(dec_site(l, CA_OUT)), d);
       SDVG_CK(g.gemm(g.attn, L.ca.out, Mt, eo2, st));
       SDVG_CK(ln_fwd(s.y2, Mt, St, L.n2, s.x2, g.xt.p, s.st2, st));
       Epilogue e1 = plain(s.h, g.cfg.dim_feedforward); e1.relu = 1;
       e1.out_hi = g.ffh.p.hi; e1.out_lo = g.ffh.p.lo; e1.ld16 = g.ffh.p.ld;
+      set_drop(e1, drop_at(dec_site(l, FF_H)), g.cfg.dim_feedforward);
       SDVG_CK(g.gemm(g.xt, L.ff1, Mt, e1, st));
       Epilogue e2 = plain(s.y3, d); e2.residual = s.x2; e2.ld_res = d;
+      set_drop(e2, drop_at(dec_site(l, FF_OUT)), d);
       SDVG_CK(g.gemm(g.ffh, L.ff2, Mt, e2, st));
       SDVG_CK(ln_fwd(s.y3, Mt, St, L.n3, xd[l + 1], g.xt.p, s.st3, st));
       y = &g.xt;
@@ -516,21 +571,23 @@ class Trainer {
       const DecLayer& L = g.dec[l]; const TDec& T = tdec[l]; const DecSave& s = sd[l];
       // x_out = LN3(y3), y3 = x2 + FFN(x2)
       SDVG_CK(ln_bwd(gin, s.y3, s.st3, L.n3, T.n3, Mt, gtmp, st));                       // gtmp = dy3
-      SDVG_CK(linear_bwd(T.ff2, gtmp, d, s.h, Mt, gWide, nullptr, st, s.h, ff));         // gWide = dh (ReLU-gated)
+      const float ds = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+      SDVG_CK(linear_bwd(T.ff2, gtmp, d, s.h, Mt, gWide, nullptr, st, s.h, ff, nullptr, drop_at(dec_site(l, FF_OUT)), ds));   // gWide = dh (ReLU / dropout gated)
       SDVG_CK(linear_bwd(T.ff1, gWide, ff, s.x2, Mt, gin, gtmp, st));                    // gin = dx2 = dh W1 + dy3
       // x2 = LN2(y2), y2 = x1 + CA(x1, mem)
       SDVG_CK(ln_bwd(gin, s.y2, s.st2, L.n2, T.n2, Mt, gtmp, st));                       // gtmp = dy2
-      SDVG_CK(linear_bwd(T.ca.out, gtmp, d, s.ac, Mt, gAttn, nullptr, st));              // gAttn = d(attention output)
-      SDVG_CK(attention_bwd(s.qc, d, s.kvc, s.kvc + d, 2 * d, gAttn, gQc, d, gKvc, gKvc + d, 2 * d, B, St, Ss, 0, st));
+      SDVG_CK(linear_bwd(T.ca.out, gtmp, d, s.ac, Mt, gAttn, nullptr, st, nullptr, 0, nullptr, drop_at(dec_site(l, CA_OUT))));   // gAttn = d(attention output)
+      SDVG_CK(attention_bwd(s.qc, d, s.kvc, s.kvc + d, 2 * d, gAttn, gQc, d, gKvc, gKvc + d, 2 * d, B, St, Ss, 0, st,
+                            drop_at(dec_site(l, CA_P))));
       SDVG_CK(linear_bwd(T.ca.q, gQc, d, s.x1, Mt, gin, gtmp, st));                      // gin = dx1 = dq Wq + dy2
       if (l == Ld - 1) SDVG_CK(pack_xt(mem32, d, Ms, d, XTmem, st));   // main stream: ordered before every later ev_dy
       SDVG_CK(linear_bwd(T.ca.kv, gKvc, 2 * d, nullptr, Ms, gMem, mem_started ? gMem : nullptr, st, nullptr, 0, &XTmem));
       mem_started = true;
       // x1 = LN1(y1), y1 = x + SA(x)
       SDVG_CK(ln_bwd(gin, s.y1, s.st1, L.n1, T.n1, Mt, gtmp, st));                       // gtmp = dy1
-      SDVG_CK(linear_bwd(T.sa.out, gtmp, d, s.a, Mt, gAttn, nullptr, st));
+      SDVG_CK(linear_bwd(T.sa.out, gtmp, d, s.a, Mt, gAttn, nullptr, st, nullptr, 0, nullptr, drop_at(dec_site(l, SA_OUT))));
       SDVG_CK(attention_bwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, gAttn, gWide, 3 * d, gWide + d, gWide + 2 * d, 3 * d, B, St,
-                            St, 1, st));
+                            St, 1, st, drop_at(dec_site(l, SA_P))));
       SDVG_CK(linear_bwd(T.sa.qkv, gWide, 3 * d, xd[l], Mt, l == 0 ? gEmbT : gin, gtmp, st));   // dx = dqkv Wqkv + dy1
       if (l == 0 || (Ld - l) % layers_per_bucket == 0) SDVG_CK(announce(offset_of(L.sa.qkv.w32), st));
     }
@@ -551,7 +608,7 @@ class Trainer {
     // target embedding: emb = (x W^T + b) sqrt(d) + PE
     SDVG_CK(weight_branch_fork(st));
     SDVG_CK(weight_branch_begin(st));
-    SDVG_CK(pack_dy(gEmbT, d, Mt, d, t_emb.gb, false, st, sqrt_d, nullptr, 0, 0, false));
+    SDVG_CK(pack_dy(gEmbT, d, Mt, d, t_emb.gb, false, st, sqrt_d, nullptr, 0, 0, false, drop_at(1)));
     SDVG_CK(weight_branch(d, E, Mt, t_emb.gw, false, tgt_c, E, XT, st));
     // encoder.norm
     SDVG_CK(ln_bwd(gMem, xe[Le], st_enc, g.enc_norm, g_encnorm, Ms, gB, st));
@@ -560,18 +617,19 @@ class Trainer {
     for (int l = Le - 1; l >= 0; --l) {
       const EncLayer& L = g.enc[l]; const TEnc& T = tenc[l]; const EncSave& s = se[l];
       SDVG_CK(ln_bwd(gin, s.y2, s.st2, L.n2, T.n2, Ms, gtmp, st));                       // dy2
-      SDVG_CK(linear_bwd(T.ff2, gtmp, d, s.h, Ms, gWide, nullptr, st, s.h, ff));
+      const float ds = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+      SDVG_CK(linear_bwd(T.ff2, gtmp, d, s.h, Ms, gWide, nullptr, st, s.h, ff, nullptr, drop_at(enc_site(l, FF_OUT)), ds));
       SDVG_CK(linear_bwd(T.ff1, gWide, ff, s.x1, Ms, gin, gtmp, st));                    // dx1
       SDVG_CK(ln_bwd(gin, s.y1, s.st1, L.n1, T.n1, Ms, gtmp, st));                       // dy1
-      SDVG_CK(linear_bwd(T.sa.out, gtmp, d, s.a, Ms, gAttn, nullptr, st));
+      SDVG_CK(linear_bwd(T.sa.out, gtmp, d, s.a, Ms, gAttn, nullptr, st, nullptr, 0, nullptr, drop_at(enc_site(l, SA_OUT))));
       SDVG_CK(attention_bwd(s.qkv, 3 * d, s.qkv + d, s.qkv + 2 * d, 3 * d, gAttn, gWide, 3 * d, gWide + d, gWide + 2 * d, 3 * d, B, Ss,
-                            Ss, 0, st));
+                            Ss, 0, st, drop_at(enc_site(l, SA_P))));
       SDVG_CK(linear_bwd(T.sa.qkv, gWide, 3 * d, xe[l], Ms, gin, gtmp, st));             // dx
       if (l == 0 || (Le - l) % layers_per_bucket == 0) SDVG_CK(announce(offset_of(L.sa.qkv.w32), st));
     }
     // source embedding (same weights as the target embedding: accumulate)
     SDVG_CK(weight_branch_begin(st));
-    SDVG_CK(pack_dy(gin, d, Ms, d, t_emb.gb, true, st, sqrt_d, nullptr, 0, 0, false));
+    SDVG_CK(pack_dy(gin, d, Ms, d, t_emb.gb, true, st, sqrt_d, nullptr, 0, 0, false, drop_at(0)));
     SDVG_CK(weight_branch(d, E, Ms, t_emb.gw, true, src_c, E, XT, st));
     SDVG_CK(weight_branch_join(st));
     return announce(0, st);

@@ -123,16 +123,20 @@ class AdamTrainer:
     Data parallel (one process per GPU, ``torch.distributed`` initialised with NCCL): every rank passes its own shard
     of the global batch and ``pe_index`` = the clips' positions in the global batch; gradients are summed over ranks
     in two buckets - the decoder-side bucket is reduced while the encoder backward still runs - and Adam applies
-    their mean on every rank, so all replicas stay identical.  Dropout is the identity (see include/sdvg.h)."""
+    their mean on every rank, so all replicas stay identical.  ``dropout`` defaults to the model's ``dropout_p``
+    (see sdvg_train_set_dropout in include/sdvg.h); data-parallel ranks should pass different ``seed`` values."""
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, *, frames_to_predict=5, use_mse=True, use_L1=False,
                  use_gdl=True, lambda_gdl=1, alpha=2, use_contrastive=True, temperature=0.07, lambda_contrastive=0.1,
-                 overlap=True, layers_per_bucket=3, ignore_dropout=False):
+                 overlap=True, layers_per_bucket=3, dropout=None, seed=0):
         if use_mse and use_L1:
             raise RuntimeError("Invalid loss function combination")        # trainers/trainer.py:107-109
-        if getattr(model, "dropout_p", 0.0) > 0 and not ignore_dropout:
-            raise RuntimeError("the training step treats dropout as the identity (torch's dropout RNG stream cannot be "
-                               "reproduced); build the model with dropout_p=0 or pass ignore_dropout=True")
+        # model.train() semantics: dropout with the model's DROPOUT_P at nn.Transformer's sites.  The masks come from the
+        # library's counter-based generator (seed, step, site, element), not from torch's RNG stream.
+        self.dropout = float(getattr(model, "dropout_p", 0.0) if dropout is None else dropout)
+        self.seed = int(seed)
+        if not 0.0 <= self.dropout < 1.0:
+            raise RuntimeError("dropout probability must be in [0, 1)")
         self.model, self.lr, self.betas, self.eps = model, float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.loss_cfg = _lib.SdvgLossConfig(int(frames_to_predict), int(bool(use_mse)), int(bool(use_L1)), int(bool(use_gdl)),
                                             float(lambda_gdl), float(alpha), int(bool(use_contrastive)), float(temperature),
@@ -185,6 +189,7 @@ class AdamTrainer:
         self.model.reserve(max_clips=B, max_tokens=S)
         h = self._handle(device)
         lib = _lib.load()
+        _lib.check(lib.sdvg_train_set_dropout(h, self.dropout, self.seed), h)
         pe_ptr = None
         if pe_index is not None:
             pe_index = pe_index.to(device=device, dtype=torch.int32).contiguous()

@@ -166,6 +166,37 @@ def test_16bit_training_mode_and_errors():
         sdvg_b200.AdamTrainer(m, use_mse=True, use_L1=True)
     with pytest.raises(RuntimeError):
         tr.step(batch)                                                # CPU tensor
-    torch.manual_seed(0)
     with pytest.raises(RuntimeError):
-        sdvg_b200.AdamTrainer(sdvg_b200.Transformer(0, 64, 2, 1, 1, 0.1, frame_size=64))     # dropout > 0
+        sdvg_b200.AdamTrainer(m, dropout=1.0)
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_dropout_training_matches_oracle_under_the_same_masks(p):
+    """model.train() with DROPOUT_P > 0: the library draws its masks from a counter-based hash (include/sdvg.h,
+    sdvg_train_set_dropout); oracle/dropout.py restates that hash, so the oracle runs nn.Transformer's dropout sites
+    (embedding + PE, attention probabilities, sub-layer outputs, FFN hidden) under exactly the same masks and autograd
+    gives the reference gradients.  Two steps: the masks change with the step counter, the weights with Adam.
+    Yardstick = the float64 run of the oracle (at p = 0.5 the fp32 oracle itself is 1e-4 from it on layer-0 tensors)."""
+    from oracle import dropout as D
+    seed = 0x1234_5678_9ABC
+    m, ref = build_pair(64, 2, 2, 2, seed=5)
+    m.dropout_p = p                                   # what Transformer(..., dropout_p=p) would carry
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-3, frames_to_predict=5, seed=seed, **CASES["c5"])
+    assert tr.dropout == p
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    losses_seen = []
+    for step in (1, 2):
+        batch = OT.make_batch(4, 6, 256, seed=30 + step)
+        sd64 = {k: v.double() for k, v in sd.items()}
+        loss, pred, grads = OT.train_grads_functional(sd64, 2, batch.double(), 5, drop=D.Dropper(p, seed, step), **CASES["c5"])
+        losses = tr.step(batch.to(DEV))
+        assert abs(float(losses[0]) - float(loss)) <= 2e-5 * abs(float(loss)), step
+        assert float((tr.prediction(4, 5).cpu().double() - pred).abs().max() / pred.abs().max()) < 1e-4, step
+        for k, gr in grads.items():
+            assert float((tr.gradient(k).cpu().double() - gr).abs().max()) <= TOLG * float(gr.abs().max()) + 1e-12, (step, k)
+        losses_seen.append(float(loss))
+        tr.pull_weights()
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    # without dropout the same first batch gives a different loss (the masks really were applied)
+    l0, _, _ = OT.train_grads_functional(ref.state_dict(), 2, OT.make_batch(4, 6, 256, seed=31), 5, **CASES["c5"])
+    assert abs(float(l0) - losses_seen[0]) > 1e-3 * abs(float(l0))
