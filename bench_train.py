@@ -6,8 +6,8 @@
 
 A "step" is one iteration of Trainer.train_loop (trainers/trainer.py:123-162) on config
 11_19_wallpushups_all_losses_test: d1024 H16 12enc/12dec, E=1024, 16 clips per GPU of 6 latents (SOS + 5 frames),
-loss = MSE + GDL(alpha 2) + 0.1 BiPatchNCE, Adam lr 1e-5; synthetic latents, seeded random-init weights,
-dropout_p = 0 (see include/sdvg.h).  Weak scaling: the global batch is 16 N clips, gradients are averaged over
+loss = MSE + GDL(alpha 2) + 0.1 BiPatchNCE, Adam lr 1e-5, dropout 0.1 (DROPOUT_P of the config; ours draws its masks
+from the library's counter-based generator, the CPU arm from torch's); synthetic latents, seeded random-init weights.  Weak scaling: the global batch is 16 N clips, gradients are averaged over
 ranks (NCCL all-reduce of the flat fp32 gradient vector in two buckets, the first overlapped with the encoder
 backward).  value = clips/s with the batch resident in HBM; e2e = the same with the batch copied from pinned host
 memory and the loss read back every step.  The step is HBM-bound (M = 80..96 rows per GEMM): the roofline is the
@@ -36,6 +36,7 @@ def parse():
     p.add_argument("--batch", type=int, default=16, help="clips per GPU (BATCH_SIZE of the config)")
     p.add_argument("--precision", default="fp32", choices=["fp32", "fp16", "bf16", "mixed"])
     p.add_argument("--no-overlap", action="store_true")
+    p.add_argument("--no-dropout", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -52,8 +53,8 @@ def cpu_step(cfg, E, batch, steps):
     from oracle import train as OT
     from oracle.ref_module import RefTransformer
     torch.manual_seed(0)
-    ref = RefTransformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"], 0.0,
-                         frame_size=cfg["frame_size"])
+    ref = RefTransformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"],
+                         cfg["dropout_p"], frame_size=cfg["frame_size"])
     opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
     times = []
     for i in range(steps + 1):
@@ -74,9 +75,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     metric, unit = "train_clips_per_sec", "clips/s"
     workload = (f"{a.config} training step: {a.batch} clips/GPU x {max(world, 1)} GPU, S_src 6 / S_tgt 5, "
-                "MSE+GDL(2)+0.1 BiPatchNCE, Adam")
+                "MSE+GDL(2)+0.1 BiPatchNCE, Adam, dropout " + ("0" if a.no_dropout else str(cfg["dropout_p"])))
     base = {"metric": metric, "unit": unit, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "data": "synthetic", "config": {"workload": workload, "arch": cfg, "clips_per_gpu": a.batch}}
+            "data": "synthetic", "config": {"workload": workload, "arch": cfg, "clips_per_gpu": a.batch,
+                                                     "dropout": 0.0 if a.no_dropout else cfg["dropout_p"]}}
     if a.impl == "reference":
         if rank != 0:
             return
@@ -98,10 +100,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)      # same weights on every rank (and as the CPU arm: the module initialises like the reference)
-    m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"], 0.0,
-                              frame_size=cfg["frame_size"], precision=a.precision)
+    m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"],
+                              cfg["dropout_p"], frame_size=cfg["frame_size"], precision=a.precision)
     m = m.to(dev)
-    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, overlap=not a.no_overlap, **LOSS)
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, overlap=not a.no_overlap, seed=1234 + rank,
+                               dropout=0.0 if a.no_dropout else None, **LOSS)
     def make_batch(seed):     # latents like encode_batch(..., use_sos=True): SOS frame of 2.0 + 5 unit-variance frames
         x = torch.randn(a.batch, 6, E, generator=torch.Generator().manual_seed(seed))
         x[:, 0] = 2.0
