@@ -23,6 +23,8 @@
 
 namespace sdvg {
 
+#define SDVG_CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return _e; } while (0)
+
 enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_SIMT = 1, KC_ATTN = 2, KC_LN = 3, KC_PACK = 4 };
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -107,6 +109,12 @@ class Engine {
   uint16_t* qkv16 = nullptr;  // [max_rows][3d] 16-bit Q|K|V of layers >= 1 (16-bit precision modes)
   uint16_t* qc16 = nullptr;   // [max_rows][d]   cross-attention Q
   uint16_t* kvc16 = nullptr;  // [max_rows][2d]  cross-attention K|V
+  // cross-attention K|V of ALL decoder layers in one GEMM (they all read the same encoder memory): stacked weight
+  // planes [Ld * 2d][d] + bias, output planes [max_rows][Ld * 2d]; 16-bit modes only (SDVG_BATCH_CROSS=0 disables)
+  Linear ca_kv_all;
+  float* ca_bias_all = nullptr;
+  uint16_t* kvc16_all = nullptr;
+  bool batch_cross = true;
   float* hist = nullptr;     // rollout history [max_clips][max_history][E]
   // token-local caches of the rollout, indexed by (clip, history slot): the embedding and the layer-0 Q/K/V of
   // encoder and decoder self-attention depend on one token only (SURVEY.md fact 5 - the only K/V that can be
@@ -377,6 +385,17 @@ class Engine {
           (e = dalloc(&qc16, static_cast<size_t>(max_rows) * d)) != cudaSuccess ||
           (e = dalloc(&kvc16, static_cast<size_t>(max_rows) * 2 * d)) != cudaSuccess)
         return fail_cuda(e, "workspace alloc qkv16");
+      if (const char* v = std::getenv("SDVG_BATCH_CROSS")) batch_cross = std::atoi(v) != 0;
+      const int Ld = c.num_decoder_layers;
+      if (batch_cross && Ld >= 2 && !split_all()) {
+        ca_kv_all.N = Ld * 2 * d; ca_kv_all.K = d; ca_kv_all.split = false;
+        if ((e = alloc_planes(ca_kv_all.p, Ld * 2 * d, d, false, true)) != cudaSuccess ||
+            (e = dalloc(&ca_bias_all, static_cast<size_t>(Ld) * 2 * d)) != cudaSuccess ||
+            (e = dalloc(&kvc16_all, static_cast<size_t>(max_rows) * Ld * 2 * d)) != cudaSuccess)
+          return fail_cuda(e, "workspace alloc stacked cross-attention K|V");
+        if (!map_planes(ca_kv_all.p, true)) return fail(SDVG_ERR_CUDA, "cuTensorMapEncodeTiled failed (stacked cross-attention weights)");
+        ca_kv_all.bias = ca_bias_all;
+      }
     }
     if (c.max_history > 0) {
       const size_t slots_total = static_cast<size_t>(c.max_clips) * c.max_history;
@@ -418,6 +437,19 @@ class Engine {
     return SDVG_OK;
   }
 
+  // copy every decoder layer's cross-attention K|V weight planes and bias into the stacked operand
+  cudaError_t restack_cross(cudaStream_t st) {
+    if (!ca_kv_all.p.hi) return cudaSuccess;
+    const int d = cfg.dim_model;
+    for (size_t l = 0; l < dec.size(); ++l) {
+      const Linear& kv = dec[l].ca.kv;
+      SDVG_CK(cudaMemcpy2DAsync(ca_kv_all.p.hi + l * 2 * d * static_cast<size_t>(ca_kv_all.p.ld), ca_kv_all.p.ld * 2, kv.p.hi,
+                                kv.p.ld * 2, static_cast<size_t>(d) * 2, 2 * d, cudaMemcpyDeviceToDevice, st));
+      SDVG_CK(cudaMemcpyAsync(ca_bias_all + l * 2 * d, kv.bias, static_cast<size_t>(2 * d) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return cudaSuccess;
+  }
+
   int finalize(cudaStream_t st) {
     if (finalized) return SDVG_OK;
     for (auto& s : slots)
@@ -435,7 +467,8 @@ class Engine {
         if (e != cudaSuccess) return fail_cuda(e, "weight pack");
       }
     }
-    cudaError_t e = cudaStreamSynchronize(st);
+    cudaError_t e = restack_cross(st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail_cuda(e, "finalize sync");
     finalized = true;
     return SDVG_OK;
@@ -680,14 +713,13 @@ class Engine {
     return pack(a, st);
   }
 
-#define SDVG_CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return _e; } while (0)
 
   // One pass of the model on operand buffers lat_s (and lat_t unless `same`).  `oe` describes where the
   // output latents go (fp32 destination, row mapping).
   // Last decoder layer for the last token of every clip (see run_model).  Input stream: xt (all Mt rows, layer
   // >= 1 so it is the LayerNorm'd stream).  Compact per-clip rows live in the first B rows of xt / ybuf / attn / ffh.
   cudaError_t pruned_last_layer(const DecLayer& L, int B, int Ss, int St, int mask_kind, const float* mask, Epilogue oe,
-                                cudaStream_t st) {
+                                cudaStream_t st, const uint16_t* kv_all = nullptr, int kv_all_ld = 0) {
     const int d = cfg.dim_model, hd = d / cfg.num_heads;
     const int Ms = B * Ss, Mt = B * St;
     // self-attention: K|V for every row, Q for the last row of each clip only
@@ -719,7 +751,12 @@ class Engine {
     SDVG_CK(layernorm(ybuf, B, L.n1, nullptr, xt, true, 1, 0, st));          // xt rows [0, B): compact stream
     // cross attention: one query per clip, K/V from the whole encoder memory
     Epilogue eq2, ekv2;
-    if (qkv16 && attention16_supported(hd, 1, Ss, 0)) {
+    if (kv_all) {   // K|V of this layer were produced by the stacked cross-attention GEMM (run_model)
+      eq2.out_hi = qc16; eq2.ld16 = d;
+      SDVG_CK(gemm(xt, L.ca.q, B, eq2, st));
+      SDVG_CK(attention(reinterpret_cast<const float*>(qc16), d, reinterpret_cast<const float*>(kv_all),
+                        reinterpret_cast<const float*>(kv_all + d), kv_all_ld, B, 1, Ss, 0, nullptr, 0, attn, st, 0, 0, true));
+    } else if (qkv16 && attention16_supported(hd, 1, Ss, 0)) {
       eq2.out_hi = qc16; eq2.ld16 = d;
       SDVG_CK(gemm(xt, L.ca.q, B, eq2, st));
       ekv2.out_hi = kvc16; ekv2.ld16 = 2 * d;
@@ -894,16 +931,33 @@ class Engine {
     // self-attention K/V need every row, but Q, both out-projections, the cross-attention query, the FFN, the
     // final norms and the output projection are computed for the last token of each clip only (M = B rows).
     const bool prune = (oe.row_map == 2) && Ld >= 2 && St >= 2 && use_prune;
+    // every decoder layer's cross-attention K|V projection reads the same encoder memory: one GEMM with the stacked
+    // weights (N = Ld * 2d: 34 waves of 256x256 tiles instead of 8 launches of 4.3 waves each)
+    const int kv_all_ld = Ld * 2 * d;
+    const bool cross_batched = kvc16_all && qkv16 && attention16_supported(hd, St, Ss, 0) &&
+                               (!prune || attention16_supported(hd, 1, Ss, 0));
+    if (cross_batched) {
+      Epilogue ekv_all;
+      ekv_all.out_hi = kvc16_all; ekv_all.ld16 = kv_all_ld;
+      SDVG_CK(gemm(mem, ca_kv_all, Ms, ekv_all, st));
+    }
     for (int l = 0; l < Ld; ++l) {
       if (prune && l == Ld - 1) {
-        SDVG_CK(pruned_last_layer(dec[l], B, Ss, St, mask_kind, mask, oe, st));
+        SDVG_CK(pruned_last_layer(dec[l], B, Ss, St, mask_kind, mask, oe, st,
+                                  cross_batched ? kvc16_all + static_cast<size_t>(l) * 2 * d : nullptr, kv_all_ld));
         return cudaSuccess;
       }
       if (cs && l == 0) SDVG_CK(self_attention_cached(c_qkv_d, rs, dec[l].sa, St, Mt, mask_kind, dec[l].n1, xt));
       else SDVG_CK(self_attention(*y, rs, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt, l == 0, true));
       // cross attention: Q from the target stream, K/V from the encoder memory
       Epilogue eq, ekv;
-      if (qkv16 && attention16_supported(hd, St, Ss, 0)) {
+      if (cross_batched) {
+        eq.out_hi = qc16; eq.ld16 = d;
+        SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
+        const uint16_t* kv = kvc16_all + static_cast<size_t>(l) * 2 * d;
+        SDVG_CK(attention(reinterpret_cast<const float*>(qc16), d, reinterpret_cast<const float*>(kv),
+                          reinterpret_cast<const float*>(kv + d), kv_all_ld, B, St, Ss, 0, nullptr, 0, attn, st, 0, 0, true));
+      } else if (qkv16 && attention16_supported(hd, St, Ss, 0)) {
         eq.out_hi = qc16; eq.ld16 = d;
         SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
         ekv.out_hi = kvc16; ekv.ld16 = 2 * d;

@@ -277,6 +277,7 @@ class Trainer {
       SDVG_CK(launch_pack_t(a, st));
     }
     wt_stale = false;
+    if (forward_planes) SDVG_CK(g.restack_cross(st));   // the rollout path's stacked cross-attention operand follows the weights
     return cudaSuccess;
   }
 

@@ -307,6 +307,22 @@ def test_tensor_core_attention_windows(monkeypatch):
         assert maxrel(outs[("1",) + k], outs[("0",) + k]) < 2e-3, k
 
 
+def test_stacked_cross_attention_projection_is_bit_identical(monkeypatch):
+    """16-bit modes project the cross-attention K|V of all decoder layers in one GEMM against stacked weights (they all
+    read the same encoder memory).  Same bits as one GEMM per layer (SDVG_BATCH_CROSS=0), for pruned and full passes."""
+    g = load_golden("small_rollout")
+    ctx = torch.randn(70, 7, 256, generator=torch.Generator().manual_seed(23)).to(DEV)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SDVG_BATCH_CROSS", flag)
+        for prec in ("mixed", "fp16"):
+            m, _ = ours_from(g, prec)
+            outs[flag, prec, "roll"] = sdvg_b200.rollout(m, ctx, 3, 5)
+            outs[flag, prec, "fwd"] = m(ctx[:64, :6].contiguous(), ctx[:64, :5].contiguous(), "causal")
+    for k in [k[1:] for k in outs if k[0] == "1"]:
+        assert torch.equal(outs[("1",) + k], outs[("0",) + k]), k
+
+
 def test_edge_shapes():
     """Single clip, single token, window longer than the history, maximum batch of the reference (64), 32-token window."""
     g = load_golden("small_rollout")
