@@ -145,6 +145,7 @@ class AdamTrainer:
         self.layers_per_bucket = int(layers_per_bucket)
         self._comm_stream = None
         self._cb = None
+        self._handle_seen = None
         self.steps = 0
 
     # -- views of library-owned memory
@@ -188,6 +189,10 @@ class AdamTrainer:
         y_expected = new_batch[:, 1:].permute(1, 0, 2).contiguous()                # :129-132
         self.model.reserve(max_clips=B, max_tokens=S)
         h = self._handle(device)
+        if self.steps > 0 and self.model._handle_key != self._handle_seen:
+            raise RuntimeError("the engine was rebuilt after training started (larger batch / window, new precision or device): "
+                               "the Adam moments lived in the old engine; reserve() the largest shapes before the first step")
+        self._handle_seen = self.model._handle_key       # (device, precision, limits, architecture) the engine was built for
         lib = _lib.load()
         _lib.check(lib.sdvg_train_set_dropout(h, self.dropout, self.seed), h)
         pe_ptr = None
@@ -237,11 +242,12 @@ class AdamTrainer:
                     w.wait()
         _lib.check(lib.sdvg_train_adam_step(h, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / world, sp), h)
         self.steps += 1
-        self._dirty = True
+        self.model._pending_pull = self          # Transformer.state_dict() copies the trained weights back on demand
         return losses
 
     def pull_weights(self):
         """Copy the trained parameters back into the module (``model.state_dict()`` for torch.save, :294)."""
+        self.model._pending_pull = None
         device = next(self.model.parameters()).device
         h = self._handle(device)
         lib = _lib.load()

@@ -59,6 +59,15 @@ class Transformer(nn.Module):
                 t.encoder.layers[0].linear1.out_features if len(t.encoder.layers) else
                 t.decoder.layers[0].linear1.out_features)
 
+    def state_dict(self, *args, **kwargs):
+        """nn.Module.state_dict; after AdamTrainer steps the trained values live in the engine, so they are copied back
+        into the parameters first (torch.save(model.state_dict()), trainers/trainer.py:294, sees the trained weights)."""
+        pending = getattr(self, "_pending_pull", None)
+        if pending is not None:
+            self._pending_pull = None
+            pending.pull_weights()
+        return super().state_dict(*args, **kwargs)
+
     def _stamp(self):
         sd = self.state_dict()
         return tuple((k, v.data_ptr(), v._version) for k, v in sd.items())

@@ -127,6 +127,34 @@ def test_c5_architecture_step_vs_oracle():
         assert ours <= TOLG + 2.0 * ref32, (k, ours, ref32)
 
 
+def test_trained_weights_reach_state_dict_and_inference():
+    """After AdamTrainer steps, model.state_dict() (torch.save at trainers/trainer.py:294) returns the trained values
+    without an explicit pull, the eval-mode forward uses them, and growing the batch after training started raises
+    instead of silently dropping the Adam moments."""
+    m, ref = build_pair(64, 2, 1, 2, seed=9)
+    _, ref0 = build_pair(64, 2, 1, 2, seed=9)                       # stays at the initial weights
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-2, frames_to_predict=5, **CASES["c5"])
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    batch = OT.make_batch(4, 6, 256, seed=2)
+    before = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    OT.train_step_ref(ref, opt, batch, 5, **CASES["c5"])
+    tr.step(batch.to(DEV))
+    sd = m.state_dict()                                             # no pull_weights() call
+    moved = max(float((sd[k].cpu() - before[k]).abs().max()) for k in before)
+    assert moved > 5e-3
+    big = [k for k, p in ref.named_parameters()]
+    assert max(float((sd[k].cpu() - ref.state_dict()[k]).abs().max()) for k in big) <= 2.1e-2   # same +-lr steps
+    x = batch[:, :5].contiguous().to(DEV)
+    ref.eval(); ref0.eval(); m.eval()
+    with torch.no_grad():
+        want = ref(x.cpu(), x.cpu(), ref.get_tgt_mask(5))
+        stale = ref0(x.cpu(), x.cpu(), ref.get_tgt_mask(5))
+        got = m(x, x, "causal").cpu()
+    assert float((got - want).abs().max()) < 0.25 * float((got - stale).abs().max())   # trained, not the initial, weights
+    with pytest.raises(RuntimeError, match="rebuilt"):
+        tr.step(OT.make_batch(m._limits["max_clips"] + 8, 6, 256, seed=3).to(DEV))
+
+
 def test_data_parallel_shards_equal_global_batch():
     """Two replicas, each with half of the clips and pe_index = global positions: the mean of their gradients is the
     gradient of the global batch (what the NCCL all-reduce + 1/world Adam step computes), SURVEY.md 8(e)."""
