@@ -48,7 +48,9 @@ def parse():
     p.add_argument("--precision", default="mixed", choices=["fp32_simt", "fp32", "fp16", "bf16", "mixed"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-steps", type=int, default=2)
-    return p.parse_args()
+    p.add_argument("--workload", default="rollout", choices=["rollout", "train"],
+                   help="train: the data-parallel training step of BASELINE configs[4] (same as bench_train.py)")
+    return p.parse_known_args()[0]
 
 
 def flops_per_clip_step(cfg, E, W):
@@ -302,6 +304,12 @@ def run_ours(a, cfg, E):
 
 def main():
     a = parse()
+    if a.workload == "train":
+        import bench_train
+        argv = ["--gpus", str(a.gpus), "--steps", str(a.steps), "--warmup", str(a.warmup), "--impl", a.impl]
+        if a.no_cpu_baseline:
+            argv.append("--no-cpu-baseline")
+        return bench_train.main(argv)
     import sdvg_b200
     cfg = {k: v for k, v in sdvg_b200.CONFIGS[a.config].items()}
     E = sdvg_b200.latent_dim(cfg["frame_size"])

@@ -26,7 +26,7 @@ LOSS = dict(use_mse=True, use_L1=False, use_gdl=True, lambda_gdl=1, alpha=2, use
             lambda_contrastive=0.1)
 
 
-def parse():
+def parse(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=20)
@@ -38,7 +38,7 @@ def parse():
     p.add_argument("--no-overlap", action="store_true")
     p.add_argument("--no-dropout", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    return p.parse_args()
+    return p.parse_args(argv)
 
 
 def param_count(cfg, E):
@@ -65,8 +65,8 @@ def cpu_step(cfg, E, batch, steps):
     return sum(times[1:]) / steps
 
 
-def main():
-    a = parse()
+def main(argv=None):
+    a = parse(argv)
     import torch
     import sdvg_b200
     cfg = sdvg_b200.CONFIGS[a.config]
