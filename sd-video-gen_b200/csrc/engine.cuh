@@ -187,6 +187,9 @@ class Engine {
     (void)weight;
     return cudaSuccess;
   }
+  // The maps cover exactly p.cols columns: a K block that reaches past them is zero-filled by TMA, which matters for
+  // column sub-views of a wider matrix (the transposed in-proj views of the training step) and for plane buffers
+  // that are shared between widths.
   bool map_planes(Planes& p, bool weight) {
     // lo planes are always fp16; hi planes follow the mode
     if (!weight) {
@@ -194,16 +197,16 @@ class Engine {
       // would otherwise stream 128 rows of A per K block to use 40 of them (a_box_slot)
       for (int s = 0; s < 3; ++s) {
         const int box = kTcBM >> s;
-        if (!make_tmap_2d(&p.tm_hi[s], p.hi, p.rows, p.ld, p.ld, box, bf16())) return false;
-        if (p.lo && !make_tmap_2d(&p.tm_lo[s], p.lo, p.rows, p.ld, p.ld, box, false)) return false;
+        if (!make_tmap_2d(&p.tm_hi[s], p.hi, p.rows, p.cols, p.ld, box, bf16())) return false;
+        if (p.lo && !make_tmap_2d(&p.tm_lo[s], p.lo, p.rows, p.cols, p.ld, box, false)) return false;
       }
       return true;
     }
     for (int i = 0; i < kNumBoxes; ++i) {
       if (kBoxRows[i] > p.rows && i > 0) { p.tm_hi[i] = p.tm_hi[i - 1]; p.tm_lo[i] = p.tm_lo[i - 1]; continue; }
       const int box = kBoxRows[i] > p.rows ? p.rows : kBoxRows[i];
-      if (!make_tmap_2d(&p.tm_hi[i], p.hi, p.rows, p.ld, p.ld, box, bf16())) return false;
-      if (p.lo && !make_tmap_2d(&p.tm_lo[i], p.lo, p.rows, p.ld, p.ld, box, false)) return false;
+      if (!make_tmap_2d(&p.tm_hi[i], p.hi, p.rows, p.cols, p.ld, box, bf16())) return false;
+      if (p.lo && !make_tmap_2d(&p.tm_lo[i], p.lo, p.rows, p.cols, p.ld, box, false)) return false;
     }
     return true;
   }

@@ -127,6 +127,21 @@ def test_c5_architecture_step_vs_oracle():
         assert ours <= TOLG + 2.0 * ref32, (k, ours, ref32)
 
 
+def test_odd_widths_and_head_sizes():
+    """d = 96 with 4 heads (head dim 24: not a multiple of 32, operand planes padded 96 -> 128 columns, 96-row weight
+    tiles) and d = 32 with 4 heads (head dim 8), one encoder / zero... one decoder layer, 3-token windows."""
+    for (d, H, Le, Ld, B, S, P) in ((96, 4, 1, 1, 3, 6, 5), (32, 4, 2, 1, 2, 4, 2)):
+        m, ref = build_pair(d, H, Le, Ld, seed=12)
+        tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=P, **CASES["c5"])
+        opt = torch.optim.Adam(ref.parameters(), lr=1e-5)
+        batch = OT.make_batch(B, S, 256, seed=13)
+        loss, pred, grads = OT.train_step_ref(ref, opt, batch, P, **CASES["c5"])
+        losses = tr.step(batch.to(DEV))
+        assert abs(float(losses[0]) - float(loss)) <= 2e-5 * abs(float(loss)), d
+        for k, gr in grads.items():
+            assert float((tr.gradient(k).cpu() - gr).abs().max()) <= TOLG * float(gr.abs().max()) + 1e-12, (d, k)
+
+
 def test_trained_weights_reach_state_dict_and_inference():
     """After AdamTrainer steps, model.state_dict() (torch.save at trainers/trainer.py:294) returns the trained values
     without an explicit pull, the eval-mode forward uses them, and growing the batch after training started raises
@@ -174,6 +189,19 @@ def test_data_parallel_shards_equal_global_batch():
     for k, gr in grads.items():
         mean = 0.5 * (shard_grads[0][k] + shard_grads[1][k]).cpu()
         assert float((mean - gr).abs().max()) <= TOLG * float(gr.abs().max()), k
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 2e-2), ("bf16", 1e-1)])
+def test_other_16bit_training_modes_run(precision, tol):
+    """fp16 / bf16 operand planes everywhere (bf16 has 8 significant bits: loose bound, it is not a parity mode)."""
+    m, ref = build_pair(64, 2, 1, 1, seed=8, precision=precision)
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, **CASES["c5"])
+    batch = OT.make_batch(3, 6, 256, seed=3)
+    loss, _, grads = OT.train_step_ref(ref, torch.optim.Adam(ref.parameters(), lr=1e-5), batch, 5, **CASES["c5"])
+    losses = tr.step(batch.to(DEV))
+    assert abs(float(losses[0]) - float(loss)) <= tol * abs(float(loss))
+    for k, gr in grads.items():
+        assert float((tr.gradient(k).cpu() - gr).norm()) <= 5 * tol * float(gr.norm()) + 1e-12, k
 
 
 def test_16bit_training_mode_and_errors():
