@@ -323,6 +323,27 @@ def test_stacked_cross_attention_projection_is_bit_identical(monkeypatch):
         assert torch.equal(outs[("1",) + k], outs[("0",) + k]), k
 
 
+@pytest.mark.parametrize("d,H", [(96, 4), (32, 4), (192, 2)])
+def test_odd_model_widths(d, H):
+    """Widths that are not multiples of 64 (operand planes padded to 64 columns, partial K blocks zero-filled by TMA)
+    and head sizes 24 / 8 / 96 (generic attention kernels): forward and rollout against the oracle, fp32 and mixed."""
+    from oracle.ref_module import RefTransformer
+    torch.manual_seed(31)
+    ref = RefTransformer(0, d, H, 2, 2, 0.1, frame_size=64).eval()
+    ctx = torch.randn(5, 7, 256, generator=torch.Generator().manual_seed(32))
+    with torch.no_grad():
+        want = R.rollout_ref(ref, ctx, 3, 5)
+        fwd = ref(ctx[:, :6], ctx[:, :5], ref.get_tgt_mask(5))
+    m = sdvg_b200.Transformer(0, d, H, 2, 2, 0.1, frame_size=64, precision="fp32")
+    m.load_state_dict(ref.state_dict())
+    m = m.eval().to(DEV)
+    assert R.max_rel_per_frame(sdvg_b200.rollout(m, ctx.to(DEV), 3, 5).cpu(), want).max() < TOL32
+    assert maxrel(m(ctx[:, :6].contiguous().to(DEV), ctx[:, :5].contiguous().to(DEV), "causal"), fwd) < TOL32
+    m.set_precision("mixed")
+    tf = sdvg_b200.rollout(m, ctx.to(DEV), 3, 5, teacher=want.to(DEV)).cpu()
+    assert R.max_rel_per_frame(tf, want).max() < TOL16
+
+
 def test_edge_shapes():
     """Single clip, single token, window longer than the history, maximum batch of the reference (64), 32-token window."""
     g = load_golden("small_rollout")
