@@ -190,6 +190,25 @@ def test_large_training_batch_takes_the_multi_tile_paths():
         assert strict_seen, B
 
 
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_long_training_windows(p):
+    """12 latents per clip (S_src 12 / S_tgt 11: the 16-token instantiations of the attention kernels), loss on the
+    last 7 positions, with and without dropout (same-mask oracle)."""
+    from oracle import dropout as D
+    m, ref = build_pair(64, 2, 1, 1, seed=16)
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=7, dropout=p, seed=99, **CASES["c5"])
+    batch = OT.make_batch(3, 12, 256, seed=17)
+    sd64 = {k: v.double() for k, v in ref.state_dict().items()}
+    loss, pred, grads = OT.train_grads_functional(sd64, 2, batch.double(), 7, drop=D.Dropper(p, 99, 1) if p else None, **CASES["c5"])
+    losses = tr.step(batch.to(DEV))
+    assert abs(float(losses[0]) - float(loss)) <= 2e-5 * abs(float(loss))
+    for k, gr in grads.items():
+        assert float((tr.gradient(k).cpu().double() - gr).abs().max()) <= TOLG * float(gr.abs().max()) + 1e-12, k
+    with pytest.raises(RuntimeError):
+        tr2 = sdvg_b200.AdamTrainer(build_pair(64, 2, 1, 1, seed=16)[0], frames_to_predict=5, **CASES["c5"])
+        tr2.step(OT.make_batch(2, 18, 256, seed=1).to(DEV))          # 18 tokens > 16
+
+
 def test_trained_weights_reach_state_dict_and_inference():
     """After AdamTrainer steps, model.state_dict() (torch.save at trainers/trainer.py:294) returns the trained values
     without an explicit pull, the eval-mode forward uses them, and growing the batch after training started raises
