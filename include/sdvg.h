@@ -218,6 +218,13 @@ int sdvg_train_prediction(sdvg_handle* h, const float** pred);
  * parameter, using grad_mul * gradient (1 / world_size after a sum all-reduce), then rebuilds the operand planes. */
 int sdvg_train_adam_step(sdvg_handle* h, float lr, float beta1, float beta2, float eps, float grad_mul, void* stream);
 
+/* The same update for the parameters [offset, offset + count) only - the ranges announced by the gradient-ready
+ * callback - so the update (and plane rebuild) of finished layers overlaps the rest of the backward pass.  The first
+ * range of a training step passes begin_step = 1 (advances the bias-correction step), the others 0; ranges must
+ * arrive from the end of the vector to its start and tile it (the last one starts at offset 0). */
+int sdvg_train_adam_step_range(sdvg_handle* h, float lr, float beta1, float beta2, float eps, float grad_mul, int64_t offset,
+                               int64_t count, int32_t begin_step, void* stream);
+
 /* Reads a parameter back (state_dict()[key], for torch.save at trainers/trainer.py:294): `out` is host or device
  * fp32 with room for the entry.  Synchronises `stream`. */
 int sdvg_get_weight(sdvg_handle* h, const char* key, float* out, void* stream);

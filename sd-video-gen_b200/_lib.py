@@ -15,7 +15,7 @@ SYMBOLS = (
     "sdvg_version", "sdvg_last_error", "sdvg_create", "sdvg_destroy", "sdvg_workspace_bytes", "sdvg_set_weight",
     "sdvg_num_weights", "sdvg_weight_key", "sdvg_finalize_weights", "sdvg_forward", "sdvg_rollout",
     "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm", "sdvg_criterion",
-    "sdvg_train_backward", "sdvg_train_gradients", "sdvg_train_set_ready_callback", "sdvg_train_set_dropout", "sdvg_param_range", "sdvg_train_prediction", "sdvg_train_adam_step",
+    "sdvg_train_backward", "sdvg_train_gradients", "sdvg_train_set_ready_callback", "sdvg_train_set_dropout", "sdvg_param_range", "sdvg_train_prediction", "sdvg_train_adam_step", "sdvg_train_adam_step_range",
     "sdvg_get_weight",
 )
 
@@ -83,6 +83,7 @@ def load(build_if_missing=True):
     lib.sdvg_param_range.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.sdvg_train_prediction.argtypes = [vp, C.POINTER(vp)]
     lib.sdvg_train_adam_step.argtypes = [vp, f32, f32, f32, f32, f32, vp]
+    lib.sdvg_train_adam_step_range.argtypes = [vp, f32, f32, f32, f32, f32, C.c_int64, C.c_int64, i32, vp]
     lib.sdvg_get_weight.argtypes = [vp, C.c_char_p, vp, vp]
     _lib = lib
     return lib

@@ -194,6 +194,14 @@ int sdvg_train_adam_step(sdvg_handle* h, float lr, float beta1, float beta2, flo
   return h->trainer->adam_step(lr, beta1, beta2, eps, grad_mul, static_cast<cudaStream_t>(stream));
 }
 
+int sdvg_train_adam_step_range(sdvg_handle* h, float lr, float beta1, float beta2, float eps, float grad_mul, int64_t offset,
+                               int64_t count, int32_t begin_step, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  if (!h->trainer) return h->eng.fail(SDVG_ERR_STATE, "no gradients: call sdvg_train_backward first");
+  return h->trainer->adam_step(lr, beta1, beta2, eps, grad_mul, static_cast<cudaStream_t>(stream), offset, count, begin_step != 0);
+}
+
 int sdvg_get_weight(sdvg_handle* h, const char* key, float* out, void* stream) {
   if (!h) return SDVG_ERR_INVALID;
   if (!out) return h->eng.fail(SDVG_ERR_INVALID, "null argument");

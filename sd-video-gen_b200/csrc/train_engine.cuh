@@ -263,10 +263,12 @@ class Trainer {
   // ------------------------------------------------------------------ weight planes
   bool wt_stale = true;
   // (Re)build the operand planes of every GEMM weight from the fp32 parameters: W planes [N][K] and W^T planes [K][N].
-  cudaError_t repack_weights(bool forward_planes, cudaStream_t st) {
+  cudaError_t repack_weights(bool forward_planes, cudaStream_t st, size_t lo = 0, size_t hi = ~static_cast<size_t>(0)) {
     for (size_t i = 0; i < g.slots.size(); ++i) {
       const WeightSlot& s = g.slots[i];
       if (!s.is_matrix) continue;
+      const size_t off = static_cast<size_t>(s.dev - g.arena);
+      if (off < lo || off >= hi) continue;     // only the matrices of the parameter range [lo, hi)
       PackTArgs a{};
       a.src = s.dev; a.ld_src = static_cast<int>(s.shape[1]); a.R = static_cast<int>(s.shape[0]); a.C = static_cast<int>(s.shape[1]);
       a.mul = 1.0f;
@@ -276,8 +278,10 @@ class Trainer {
       Engine::Scope sc(&g, KC_PACK, 0.0, static_cast<double>(s.count) * (forward_planes ? 12.0 : 8.0), st);
       SDVG_CK(launch_pack_t(a, st));
     }
-    wt_stale = false;
-    if (forward_planes) SDVG_CK(g.restack_cross(st));   // the rollout path's stacked cross-attention operand follows the weights
+    if (lo == 0) {   // a full rebuild, or the last range of a ranged one (ranges run from the end of the arena to its start)
+      wt_stale = false;
+      if (forward_planes) SDVG_CK(g.restack_cross(st));   // the rollout path's stacked cross-attention operand follows the weights
+    }
     return cudaSuccess;
   }
 
@@ -670,11 +674,19 @@ class Trainer {
   }
 
   // torch.optim.Adam.step() on the flat vectors, then the operand planes of every weight are rebuilt.
-  int adam_step(float lr, float beta1, float beta2, float eps, float grad_mul, cudaStream_t st) {
+  // Ranged form: parameters [offset, offset + count) only (offset a multiple of 64, as announced by the gradient-ready
+  // callback), so that the update of the layers whose gradients are final runs next to the rest of the backward pass;
+  // `begin_step` advances the step counter of the bias correction (first range of a step).
+  int adam_step(float lr, float beta1, float beta2, float eps, float grad_mul, cudaStream_t st, long long offset = 0,
+                long long count = -1, bool begin_step = true) {
     if (!ready) return g.fail(SDVG_ERR_STATE, "no gradients: call the backward pass first");
-    ++adam_t;
+    if (count < 0) count = static_cast<long long>(g.arena_count) - offset;
+    if (offset < 0 || offset % 4 != 0 || count % 4 != 0 || offset + count > static_cast<long long>(g.arena_count))
+      return g.fail(SDVG_ERR_INVALID, "bad parameter range [%lld, +%lld)", offset, count);
+    if (begin_step) ++adam_t;
+    if (adam_t == 0) return g.fail(SDVG_ERR_STATE, "ranged Adam step without begin_step");
     AdamArgs a{};
-    a.p = g.arena; a.g = grads; a.m = adam_m; a.v = adam_v; a.n = static_cast<long long>(g.arena_count);
+    a.p = g.arena + offset; a.g = grads + offset; a.m = adam_m + offset; a.v = adam_v + offset; a.n = count;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.gmul = grad_mul;
     const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(adam_t));
     const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(adam_t));
@@ -683,9 +695,11 @@ class Trainer {
     cudaError_t e;
     {
       Engine::Scope sc(&g, KC_PACK, 0.0, 28.0 * a.n, st);
-      e = launch_kernel(adam_kernel, dim3(g.num_sms * 8), dim3(256), 0, st, a);
+      long long blocks = (count / 4 + 255) / 256;
+      if (blocks > g.num_sms * 8) blocks = g.num_sms * 8;
+      e = launch_kernel(adam_kernel, dim3(static_cast<unsigned>(blocks < 1 ? 1 : blocks)), dim3(256), 0, st, a);
     }
-    if (e == cudaSuccess) e = repack_weights(true, st);
+    if (e == cudaSuccess) e = repack_weights(true, st, static_cast<size_t>(offset), static_cast<size_t>(offset + count));
     if (e != cudaSuccess) return g.fail_cuda(e, "Adam step");
     return SDVG_OK;
   }

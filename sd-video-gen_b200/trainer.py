@@ -122,8 +122,9 @@ class AdamTrainer:
 
     Data parallel (one process per GPU, ``torch.distributed`` initialised with NCCL): every rank passes its own shard
     of the global batch and ``pe_index`` = the clips' positions in the global batch; gradients are summed over ranks
-    in two buckets - the decoder-side bucket is reduced while the encoder backward still runs - and Adam applies
-    their mean on every rank, so all replicas stay identical.  ``dropout`` defaults to the model's ``dropout_p``
+    range by range as the backward pass finishes them - reduction and Adam update of a range run on a communication
+    stream while the backward pass of the earlier layers continues - and Adam applies their mean on every rank, so all
+    replicas stay identical.  (``overlap=False``: plain backward, two-bucket all-reduce, one Adam step.)  ``dropout`` defaults to the model's ``dropout_p``
     (see sdvg_train_set_dropout in include/sdvg.h); data-parallel ranks should pass different ``seed`` values."""
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, *, frames_to_predict=5, use_mse=True, use_L1=False,
@@ -208,39 +209,48 @@ class AdamTrainer:
             _lib.check(lib.sdvg_train_backward(h, new_batch.data_ptr(), y_input.data_ptr(), y_expected.data_ptr(), B, S, S - 1,
                                                C.byref(self.loss_cfg), pe_ptr, losses.data_ptr(), part, sp), h)
 
-        if world == 1:
-            backward(0)
-        else:
-            flat, split = self.gradients(device)
-            if self.overlap:
-                # the library announces gradient ranges as the backward pass is enqueued (sdvg_train_set_ready_callback):
-                # each range is all-reduced on the communication stream while the rest of the backward still runs
-                if self._comm_stream is None:
-                    self._comm_stream = torch.cuda.Stream(device)
-                works = []
-                comm = self._comm_stream
+        adam = (self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / world)
+        if self.overlap:
+            # The library announces ranges of the flat gradient vector as soon as the backward pass - still being
+            # enqueued - has finished them (sdvg_train_set_ready_callback, from the end of the vector to its start).  Each
+            # range is all-reduced (N > 1) and Adam-updated on the communication stream while the backward pass of the
+            # earlier layers keeps running on the caller's stream: neither touches the other's weights or gradients.
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device)
+            comm = self._comm_stream
+            flat = self.gradients(device)[0] if world > 1 else None
+            state = {"first": 1, "error": None}
 
-                def ready(_user, off, cnt):
+            def ready(_user, off, cnt):
+                try:
                     ev = torch.cuda.Event()
                     ev.record(stream)
                     comm.wait_event(ev)
                     with torch.cuda.stream(comm):
-                        works.append(dist.all_reduce(flat[off:off + cnt], op=dist.ReduceOp.SUM, async_op=True))
+                        if world > 1:
+                            dist.all_reduce(flat[off:off + cnt], op=dist.ReduceOp.SUM)      # stream-ordered on `comm`
+                        _lib.check(lib.sdvg_train_adam_step_range(h, *adam, off, cnt, state["first"],
+                                                                  C.c_void_p(comm.cuda_stream)), h)
+                    state["first"] = 0
+                except Exception as exc:            # an exception must not unwind through the C caller
+                    state["error"] = state["error"] or exc
 
-                self._cb = _lib.GRAD_READY_FN(ready)          # keep the ctypes thunk alive while the library holds it
-                _lib.check(lib.sdvg_train_set_ready_callback(h, self._cb, None, self.layers_per_bucket), h)
-                try:
-                    backward(0)
-                finally:
-                    _lib.check(lib.sdvg_train_set_ready_callback(h, _lib.GRAD_READY_FN(0), None, 0), h)
-                for w in works:
-                    w.wait()                                # orders the current stream after each range's reduction
-                stream.wait_stream(comm)
-            else:
+            self._cb = _lib.GRAD_READY_FN(ready)          # keep the ctypes thunk alive while the library holds it
+            _lib.check(lib.sdvg_train_set_ready_callback(h, self._cb, None, self.layers_per_bucket), h)
+            try:
                 backward(0)
+            finally:
+                _lib.check(lib.sdvg_train_set_ready_callback(h, _lib.GRAD_READY_FN(0), None, 0), h)
+            stream.wait_stream(comm)
+            if state["error"] is not None:
+                raise state["error"]
+        else:
+            backward(0)
+            if world > 1:
+                flat, split = self.gradients(device)
                 for w in allreduce_buckets(flat, split, world):
                     w.wait()
-        _lib.check(lib.sdvg_train_adam_step(h, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / world, sp), h)
+            _lib.check(lib.sdvg_train_adam_step(h, *adam, sp), h)
         self.steps += 1
         self.model._pending_pull = self          # Transformer.state_dict() copies the trained weights back on demand
         return losses

@@ -68,8 +68,12 @@ class Transformer(nn.Module):
             pending.pull_weights()
         return super().state_dict(*args, **kwargs)
 
+    def load_state_dict(self, *args, **kwargs):
+        self._pending_pull = None            # loaded values supersede whatever an AdamTrainer left in the engine
+        return super().load_state_dict(*args, **kwargs)
+
     def _stamp(self):
-        sd = self.state_dict()
+        sd = super().state_dict()       # not self.state_dict(): that one pulls trained weights back from the engine
         return tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
 
     def _free(self):
