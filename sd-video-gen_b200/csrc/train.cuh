@@ -356,6 +356,7 @@ struct AttnTrainArgs {
   float* out32; int ld32;
   uint16_t* out_hi; uint16_t* out_lo; int ld16; int bf16;
   uint32_t drop_thr, drop_key; float drop_scale;
+  int cshift;   // hd == 32 << cshift, or -1
 };
 
 __global__ void __launch_bounds__(128) attention_train_fwd_kernel(const __grid_constant__ AttnTrainArgs a) {
@@ -375,10 +376,32 @@ __global__ void __launch_bounds__(128) attention_train_fwd_kernel(const __grid_c
   float* sK = sQ + Sq * ldp;
   float* sV = sK + Sk * ldp;
   float (*P)[kTrainMaxS] = sP[wib];
-  for (int r = 0; r < Sq + 2 * Sk; ++r) {
-    const float* src = r < Sq ? q + static_cast<size_t>(r) * a.ldq : r < Sq + Sk ? k + static_cast<size_t>(r - Sq) * a.ldkv
-                                                                                 : v + static_cast<size_t>(r - Sq - Sk) * a.ldkv;
-    for (int e = lane; e < hd; e += 32) sQ[r * ldp + e] = __ldg(src + e);
+  {
+    // stage Q, K, V (smem rows in that order); hd = 32 << cshift: 16 independent loads in flight per lane
+    const int nrows = Sq + 2 * Sk;
+    auto row_ptr = [&](int r) -> const float* {
+      return r < Sq ? q + static_cast<size_t>(r) * a.ldq
+           : r < Sq + Sk ? k + static_cast<size_t>(r - Sq) * a.ldkv : v + static_cast<size_t>(r - Sq - Sk) * a.ldkv;
+    };
+    if (a.cshift >= 0) {
+      const int nchunks = nrows << a.cshift, cmask = (1 << a.cshift) - 1;
+      for (int c0 = 0; c0 < nchunks; c0 += 16) {
+        float tmp[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int ci = c0 + u;
+          tmp[u] = ci < nchunks ? __ldg(row_ptr(ci >> a.cshift) + ((ci & cmask) << 5) + lane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int ci = c0 + u;
+          if (ci < nchunks) sQ[(ci >> a.cshift) * ldp + ((ci & cmask) << 5) + lane] = tmp[u];
+        }
+      }
+    } else {
+      for (int r = 0; r < nrows; ++r)
+        for (int e = lane; e < hd; e += 32) sQ[r * ldp + e] = __ldg(row_ptr(r) + e);
+    }
   }
   __syncwarp();
   for (int p = lane; p < Sq * Sk; p += 32) {
@@ -420,7 +443,10 @@ __global__ void __launch_bounds__(128) attention_train_fwd_kernel(const __grid_c
   }
 }
 
-inline cudaError_t launch_attention_train_fwd(const AttnTrainArgs& a, cudaStream_t stream) {
+inline cudaError_t launch_attention_train_fwd(const AttnTrainArgs& a_in, cudaStream_t stream) {
+  AttnTrainArgs a = a_in;
+  a.cshift = -1;
+  for (int sft = 0; sft < 4; ++sft) if (a.hd == (32 << sft)) a.cshift = sft;
   if (a.Sq > kTrainMaxS || a.Sk > kTrainMaxS) return cudaErrorInvalidValue;
   const size_t smem = 4 * static_cast<size_t>(a.Sq + 2 * a.Sk) * (a.hd + 1) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
