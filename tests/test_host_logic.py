@@ -185,3 +185,34 @@ def test_data_parallel_gradient_buckets_gloo(tmp_path):
     got, want = torch.load(tmp)
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
+def test_dropout_hash_restatement_matches_library_header(tmp_path):
+    """oracle/dropout.py against the library's own drop_hash / drop_site_key (csrc/common.cuh, __host__ __device__):
+    a small host program is compiled with nvcc from the header and run on the CPU (no GPU involved)."""
+    import shutil
+    import subprocess
+    from oracle import dropout as D
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "h.cu"
+    src.write_text('#include <cstdio>\n#include "common.cuh"\nint main() {\n'
+                   '  const unsigned long long seeds[3] = {0ull, 0x123456789ABCull, 0xFFFFFFFFFFFFFFFFull};\n'
+                   '  for (int s = 0; s < 3; ++s) for (unsigned step = 1; step < 4; ++step) for (unsigned site : {0u, 1u, 1004u, 2115u}) {\n'
+                   '    const unsigned key = sdvg::drop_site_key(seeds[s], step, site);\n'
+                   '    printf("%u", key);\n'
+                   '    for (unsigned idx : {0u, 1u, 12345u, 4000000000u}) printf(" %u", sdvg::drop_hash(key, idx));\n'
+                   '    printf("\\n");\n  }\n  return 0;\n}\n')
+    exe = tmp_path / "h"
+    inc = os.path.join(ROOT, "sd-video-gen_b200", "csrc")
+    subprocess.run([nvcc, "-std=c++17", "-I", inc, "-o", str(exe), str(src)], check=True, capture_output=True, timeout=300)
+    lines = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=60).stdout.strip().splitlines()
+    it = iter(lines)
+    for seed in (0, 0x123456789ABC, 0xFFFFFFFFFFFFFFFF):
+        for step in (1, 2, 3):
+            for site in (0, 1, 1004, 2115):
+                got = [int(v) for v in next(it).split()]
+                key = D.site_key(seed, step, site)
+                want = [key] + [int(D.fmix32((idx * 0x9E3779B1 + key) & D.M32)) for idx in (0, 1, 12345, 4000000000)]
+                assert got == want, (seed, step, site)
