@@ -135,6 +135,10 @@ def main(argv=None):
 
     for i in range(max(3, a.warmup)):
         tr.step(devb[i % 4], pe_index=pe)
+    from bench import ClockSampler                       # nvidia-smi clocks / throttle reasons during the timed region
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     n0 = m.launch_count()
     ms = timed(lambda i: tr.step(devb[i % 4], pe_index=pe), a.steps)
     launches = (m.launch_count() - n0) // a.steps
@@ -147,6 +151,7 @@ def main(argv=None):
         torch.cuda.current_stream().synchronize()
     ms_e2e = timed(e2e_step, a.steps)
 
+    clocks = sampler.stop() if sampler else None
     # per-kernel-class device time of one step (instrumented pass, outside the timed regions)
     m.timing(True)
     tr.step(devb[0], pe_index=pe)
@@ -171,7 +176,7 @@ def main(argv=None):
            "ms_per_step": ms, "dtype": "fp16x2 split operands, fp32 accumulate" if split else a.precision,
            "e2e": {"value": a.batch * world / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": host[0].numel() * 4,
                    "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e},
-           "gpu_launches": int(launches) * a.steps,
+           "gpu_launches": int(launches) * a.steps, "clocks": clocks,
            "roofline": {"bound": "hbm", "achieved": bytes_step / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": bytes_step / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": src,
                         "algorithmic_bytes_per_step": bytes_step, "launches_per_step": int(launches), "classes_ms": classes}}
