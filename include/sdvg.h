@@ -132,9 +132,10 @@ int sdvg_rollout(sdvg_handle* h, const float* ctx, int32_t B, int32_t C, int32_t
 
 /* Per-kernel-class device timing (CUDA events around every launch of the library's kernels).  Off by default.
  * sdvg_timing_read synchronises, accumulates and clears; classes: 0 GEMM (tensor core), 1 GEMM (SIMT),
- * 2 attention, 3 LayerNorm, 4 pack/export.  flops = algorithmic 2*M*N*K of the launches (0 for non-GEMM),
- * bytes = algorithmic bytes moved by the launches. */
-#define SDVG_NUM_KERNEL_CLASSES 5
+ * 2 attention, 3 LayerNorm, 4 pack/export, 5 persistent small-batch kernel (one launch = a whole forward pass or
+ * rollout when clips x tokens <= 128; bytes = weight-plane bytes it streams, flops = 2*M*N*K of its GEMM ops).
+ * flops = algorithmic 2*M*N*K of the launches (0 for non-GEMM), bytes = algorithmic bytes moved by the launches. */
+#define SDVG_NUM_KERNEL_CLASSES 6
 int sdvg_timing_enable(sdvg_handle* h, int32_t on);
 int sdvg_timing_read(sdvg_handle* h, double* ms, int64_t* launches, double* flops, double* bytes);
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsdvg.so")
 
 PRECISIONS = {"fp32_simt": 0, "fp32": 1, "fp16": 2, "bf16": 3, "mixed": 4}
-KERNEL_CLASSES = ("gemm_tc", "gemm_simt", "attention", "layernorm", "pack")
+KERNEL_CLASSES = ("gemm_tc", "gemm_simt", "attention", "layernorm", "pack", "persistent")
 
 # every symbol include/sdvg.h declares (tests check the library exports all of them)
 SYMBOLS = (

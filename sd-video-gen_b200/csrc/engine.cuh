@@ -20,12 +20,13 @@
 #include "gemm_tc2.cuh"
 #include "layernorm.cuh"
 #include "pack.cuh"
+#include "persistent.cuh"
 
 namespace sdvg {
 
 #define SDVG_CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return _e; } while (0)
 
-enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_SIMT = 1, KC_ATTN = 2, KC_LN = 3, KC_PACK = 4 };
+enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_SIMT = 1, KC_ATTN = 2, KC_LN = 3, KC_PACK = 4, KC_PK = 5 };
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // TMA box heights (rows of W per load) we keep tensor maps for: one-CTA tiles use BN rows, pair tiles BN/2.
@@ -128,6 +129,41 @@ class Engine {
   float2* ln_stats = nullptr;  // [max_rows] (mean, rstd) left behind by the last LayerNorm kernel
   int* pe_mod64 = nullptr;   // [max_clips] b mod 64
 
+  // ---- persistent small-batch path (persistent.cuh): while pk_rec is set, gemm() / layernorm() / attention() /
+  // pack() / add_rows() append ops to pk_ops instead of launching, so run_model() and rollout_enqueue() are the one
+  // description of the model for both the per-kernel path and the one-launch path
+  bool use_pk = true;          // SDVG_PK=0 disables
+  bool pk_rec = false;
+  bool pk_bad = false;         // an op the persistent kernel cannot run was recorded: fall back to per-kernel launches
+  std::vector<PkOp> pk_ops;
+  int pk_mt_max = 0;
+  double pk_bytes = 0.0, pk_flops = 0.0;   // weight-plane bytes streamed / GEMM FLOPs of the recorded program
+  int pk_grid = -1;            // CTAs of a launch (multiple of the cluster size); -1 = not initialised, 0 = unavailable
+  unsigned int* pk_sync = nullptr;
+  CUtensorMap* pk_maps_dev = nullptr;
+  static constexpr int kPkMaxMaps = 2048;
+  struct PkMapKey {
+    const void* base; int rows, cols, ld, box, bf;
+    bool operator<(const PkMapKey& o) const {
+      if (base != o.base) return base < o.base;
+      if (rows != o.rows) return rows < o.rows;
+      if (cols != o.cols) return cols < o.cols;
+      if (ld != o.ld) return ld < o.ld;
+      if (box != o.box) return box < o.box;
+      return bf < o.bf;
+    }
+  };
+  std::map<PkMapKey, int> pk_map_index;
+  std::vector<CUtensorMap> pk_maps_host;
+  int pk_maps_uploaded = 0;
+  struct PkProgram {
+    std::vector<long long> key;   // everything the recorded ops depend on (pointers, shapes, flags)
+    PkOp* dev = nullptr; int capacity = 0;
+    int n_ops = 0; PkSmemPlan plan{}; double bytes = 0.0, flops = 0.0; int64_t stamp = 0;
+  };
+  std::vector<PkProgram> pk_programs;
+  int64_t pk_clock = 0;
+
   struct TimedSpan { cudaEvent_t a, b; int cls; double flops, bytes; };
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
@@ -161,6 +197,7 @@ class Engine {
     destroy_graphs();
     for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
+    for (auto& pr : pk_programs) if (pr.dev) cudaFree(pr.dev);
     for (void* p : allocs) cudaFree(p);
   }
 
@@ -412,6 +449,7 @@ class Engine {
         return fail_cuda(e, "cache alloc");
     }
     if (const char* v = std::getenv("SDVG_LAZY_LN")) lazy_ln = std::atoi(v) != 0;
+    if (const char* v = std::getenv("SDVG_PK")) use_pk = std::atoi(v) != 0;
     if (const char* v = std::getenv("SDVG_KSPLIT")) use_ksplit = std::atoi(v) != 0;
     if (tc() && ((e = dalloc(&ks_ws, static_cast<size_t>(num_sms) * kTcBM * 128)) != cudaSuccess ||
                  (e = dalloc(&ks_flags, 1024)) != cudaSuccess))
@@ -642,6 +680,7 @@ class Engine {
     e.bias = L.bias;
     e.bf16 = bf16();
     const double flops = 2.0 * M * L.N * L.K;
+    if (pk_rec) return pk_record_gemm(A, L, M, e);
     if (!tc()) {
       Scope sc(this, KC_GEMM_SIMT, flops, 4.0 * (double(M) * L.K + double(L.N) * L.K + double(M) * L.N), st);
       return launch_gemm_simt(A.f32, A.ld32, L.w32, L.K, M, L.N, L.K, e, st);
@@ -671,6 +710,12 @@ class Engine {
     a.out32 = (want_f32 || !tc()) ? dst.f32 : nullptr; a.ld32 = dst.ld32;
     a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
     const double d = cfg.dim_model;
+    if (pk_rec) {
+      if (a.d % 4 != 0 || a.d > 4096 || a.ldx % 4 != 0) { pk_bad = true; return cudaSuccess; }
+      PkOp op; op.type = PK_LN; op.u.ln = a;
+      pk_ops.push_back(op);
+      return cudaSuccess;
+    }
     Scope sc(this, KC_LN, 0.0, rows * d * (4.0 + (a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0)), st);
     return launch_layernorm(a, st);
   }
@@ -690,16 +735,230 @@ class Engine {
     a.out32 = tc() ? nullptr : dst.f32; a.ld32 = dst.ld32;
     a.out_hi = dst.p.hi; a.out_lo = dst.p.lo; a.ld16 = dst.p.ld; a.bf16 = bf16();
     const double d = cfg.dim_model;
+    if (pk_rec) {
+      if (Sq > kAttnMaxS || Sk > kAttnMaxS || a.hd > 256) { pk_bad = true; return cudaSuccess; }
+      if (a.q_clip_stride == 0) a.q_clip_stride = static_cast<long long>(Sq) * ldq;
+      if (a.kv_clip_stride == 0) a.kv_clip_stride = static_cast<long long>(Sk) * ldkv;
+      PkOp op; op.type = PK_ATTN; op.in16 = in16 ? 1 : 0; op.u.at = a;
+      pk_ops.push_back(op);
+      return cudaSuccess;
+    }
     Scope sc(this, KC_ATTN, 0.0,
              double(B) * d * ((in16 ? 2.0 : 4.0) * (Sq + 2.0 * Sk) + Sq * ((a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0))), st);
     return in16 ? launch_attention16(a, st) : launch_attention(a, st);
   }
 
   cudaError_t pack(const PackArgs& a, cudaStream_t st) {
+    if (pk_rec) {
+      if (a.width % 4 != 0 || a.tokens > kPackMaxTokens) { pk_bad = true; return cudaSuccess; }
+      PkOp op; op.type = PK_PACK; op.u.pk = a;
+      pk_ops.push_back(op);
+      return cudaSuccess;
+    }
     const double n = double(a.clips) * a.tokens * a.width;
     Scope sc(this, KC_PACK, 0.0, n * (4.0 + (a.out32 ? 4.0 : 0.0) + (a.out_hi ? 2.0 : 0.0) + (a.out_lo ? 2.0 : 0.0)), st);
     return launch_pack(a, num_sms, st);
   }
+
+  cudaError_t add_rows(const AddArgs& ad, cudaStream_t st) {
+    if (pk_rec) {
+      if (ad.width % 4 != 0) { pk_bad = true; return cudaSuccess; }
+      PkOp op; op.type = PK_ADD; op.u.ad = ad;
+      pk_ops.push_back(op);
+      return cudaSuccess;
+    }
+    Scope sc(this, KC_PACK, 0.0, 12.0 * ad.clips * ad.width, st);
+    return launch_add_rows(ad, num_sms, st);
+  }
+
+  // ------------------------------------------------------------------ persistent small-batch path
+  // One-time set-up: how many 8-CTA clusters of the persistent kernel the device can hold at once (one CTA per SM:
+  // the kernel uses all of shared memory), the tensor-map table and the barrier counter.
+  bool pk_init() {
+    if (pk_grid >= 0) return pk_grid > 0;
+    pk_grid = 0;
+    if (!use_pk || !get_encode_fn()) return false;
+    if (cudaFuncSetAttribute(persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    int clusters = 0;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(num_sms / kPkCluster * kPkCluster); lc.blockDim = dim3(kPkThreads); lc.dynamicSmemBytes = kTcSmemLimit;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kPkCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&clusters, persistent_kernel, &lc) != cudaSuccess) { cudaGetLastError(); return false; }
+    int want = num_sms / kPkCluster;
+    if (const char* v = std::getenv("SDVG_PK_CLUSTERS")) { const int w = std::atoi(v); if (w > 0 && w < want) want = w; }
+    if (clusters > want) clusters = want;
+    if (clusters < 1) return false;
+    if (dalloc(&pk_sync, 64) != cudaSuccess || dalloc(&pk_maps_dev, static_cast<size_t>(kPkMaxMaps)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    pk_grid = clusters * kPkCluster;
+    return true;
+  }
+
+  int pk_map(const void* base, int rows, int cols, int ld, int box_rows, bool bf) {
+    PkMapKey k{base, rows, cols, ld, box_rows, bf ? 1 : 0};
+    auto it = pk_map_index.find(k);
+    if (it != pk_map_index.end()) return it->second;
+    if (static_cast<int>(pk_maps_host.size()) >= kPkMaxMaps) return -1;
+    CUtensorMap m;
+    if (!make_tmap_2d(&m, base, rows, cols, ld, box_rows, bf)) return -1;
+    pk_maps_host.push_back(m);
+    const int idx = static_cast<int>(pk_maps_host.size()) - 1;
+    pk_map_index[k] = idx;
+    return idx;
+  }
+
+  cudaError_t pk_record_gemm(const ActBuf& A, const Linear& L, int M, const Epilogue& e) {
+    if (!tc() || M > kPkMaxRows || M <= 0 || !A.p.hi || !L.p.hi || pk_grid <= 0) { pk_bad = true; return cudaSuccess; }
+    const bool split = L.split && A.p.lo != nullptr && L.p.lo != nullptr;
+    PkOp op;
+    op.type = PK_GEMM;
+    PkGemm& g = op.u.g;
+    g.M = M; g.N = L.N; g.K = L.K; g.MT = round_up(M, 16);
+    g.split = split ? 1 : 0; g.bf16 = bf16() ? 1 : 0;
+    g.T = pk_tile_rows(L.N, pk_grid / kPkCluster);
+    g.n_tiles = ceil_div(L.N, g.T);
+    g.w_hi = pk_map(L.p.hi, L.p.rows, L.p.cols, L.p.ld, g.T, bf16());
+    g.w_lo = split ? pk_map(L.p.lo, L.p.rows, L.p.cols, L.p.ld, g.T, false) : g.w_hi;
+    g.a_hi = A.p.hi; g.a_lo = split ? A.p.lo : A.p.hi; g.lda = A.p.ld;
+    // the activation planes are read with 16-byte loads, K blocks of 64 elements, MT rows
+    if (g.w_hi < 0 || g.w_lo < 0 || A.p.rows < g.MT || A.p.cols != L.K || A.p.ld % 64 != 0 || A.p.ld < round_up(L.K, kTcBK) ||
+        reinterpret_cast<uintptr_t>(A.p.hi) % 16 != 0 || (split && reinterpret_cast<uintptr_t>(A.p.lo) % 16 != 0)) {
+      pk_bad = true;
+      return cudaSuccess;
+    }
+    g.epi = e;
+    pk_ops.push_back(op);
+    if (g.MT > pk_mt_max) pk_mt_max = g.MT;
+    pk_bytes += (split ? 2.0 : 1.0) * 2.0 * double(L.N) * round_up(L.K, kTcBK);
+    pk_flops += 2.0 * M * double(L.N) * L.K;
+    return cudaSuccess;
+  }
+
+  void pk_begin() {
+    pk_rec = true; pk_bad = false; pk_ops.clear(); pk_mt_max = 0; pk_bytes = 0.0; pk_flops = 0.0;
+  }
+
+  // Finish recording: upload the program (cached by `key`), returns the slot or nullptr when the ops cannot run
+  // in the persistent kernel.
+  PkProgram* pk_end(const std::vector<long long>& key, cudaStream_t st) {
+    pk_rec = false;
+    if (pk_bad || pk_ops.empty()) return nullptr;
+    PkProgram* slot = nullptr;
+    if (pk_programs.size() < 8) { pk_programs.emplace_back(); slot = &pk_programs.back(); }
+    else {
+      for (auto& pr : pk_programs) if (!slot || pr.stamp < slot->stamp) slot = &pr;
+    }
+    const int n = static_cast<int>(pk_ops.size());
+    if (slot->capacity < n) {
+      if (slot->dev) { cudaDeviceSynchronize(); cudaFree(slot->dev); slot->dev = nullptr; slot->capacity = 0; }
+      void* p = nullptr;
+      if (cudaMalloc(&p, static_cast<size_t>(n) * sizeof(PkOp)) != cudaSuccess) { cudaGetLastError(); slot->key.clear(); return nullptr; }
+      slot->dev = static_cast<PkOp*>(p); slot->capacity = n;
+    }
+    // (a slot being overwritten may still be read by an earlier launch of the same stream: the copy is stream-ordered)
+    if (cudaMemcpyAsync(slot->dev, pk_ops.data(), static_cast<size_t>(n) * sizeof(PkOp), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      cudaGetLastError(); slot->key.clear(); return nullptr;
+    }
+    const int nm = static_cast<int>(pk_maps_host.size());
+    if (nm > pk_maps_uploaded) {
+      if (cudaMemcpyAsync(pk_maps_dev + pk_maps_uploaded, pk_maps_host.data() + pk_maps_uploaded,
+                          static_cast<size_t>(nm - pk_maps_uploaded) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaGetLastError(); slot->key.clear(); return nullptr;
+      }
+      pk_maps_uploaded = nm;
+    }
+    slot->key = key; slot->n_ops = n; slot->plan = pk_smem_plan(pk_mt_max); slot->bytes = pk_bytes; slot->flops = pk_flops;
+    return slot;
+  }
+
+  PkProgram* pk_find(const std::vector<long long>& key) {
+    for (auto& pr : pk_programs) if (!pr.key.empty() && pr.key == key) return &pr;
+    return nullptr;
+  }
+
+  cudaError_t pk_launch(PkProgram& pr, cudaStream_t st) {
+    pr.stamp = ++pk_clock;
+    PkParams P{};
+    P.ops = pr.dev; P.n_ops = pr.n_ops; P.maps = pk_maps_dev; P.sync = pk_sync;
+    P.w_slots = pr.plan.w_slots; P.a_stages = pr.plan.a_stages; P.a_stage_bytes = pr.plan.a_stage_bytes;
+    // SDVG_PK_TRACE=<ops>[,<cta>]: per-op pipeline timestamps of one CTA, printed after the launch (debug / tuning)
+    static int trace_ops = -1, trace_cta = 0, trace_first = 0;
+    if (trace_ops < 0) {
+      trace_ops = 0;
+      if (const char* v = std::getenv("SDVG_PK_TRACE")) {
+        trace_ops = std::atoi(v);
+        if (const char* c = std::strchr(v, ',')) { trace_cta = std::atoi(c + 1); if (const char* c2 = std::strchr(c + 1, ',')) trace_first = std::atoi(c2 + 1); }
+      }
+    }
+    unsigned long long* trace_dev = nullptr;
+    if (trace_ops > 0) {
+      if (cudaMalloc(reinterpret_cast<void**>(&trace_dev), static_cast<size_t>(pr.n_ops) * 32 * 8) == cudaSuccess)
+        cudaMemsetAsync(trace_dev, 0, static_cast<size_t>(pr.n_ops) * 32 * 8, st);
+      else trace_dev = nullptr;
+    }
+    P.trace = trace_dev; P.trace_cta = trace_cta;
+    struct TraceDump {
+      Engine* g; PkProgram* pr; unsigned long long* dev; int n; int first; cudaStream_t st;
+      ~TraceDump() {
+        if (!dev) return;
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(static_cast<size_t>(pr->n_ops) * 32);
+        cudaMemcpy(h.data(), dev, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(dev);
+        unsigned long long t0 = ~0ull;
+        for (size_t i = 0; i < h.size(); ++i) if ((i & 31) != 14 && (i & 31) != 15 && h[i] && h[i] < t0 && static_cast<int>(i >> 5) >= first) t0 = h[i];
+        const int lim = first + n < pr->n_ops ? first + n : pr->n_ops;
+        std::fprintf(stderr, "pk trace (ns since first stamp): op type | - - - | MMA: - last | W: enter barrier tfull pushed reduced released | done fenced arrived\n");
+        for (int i = first; i < lim; ++i) {
+          std::fprintf(stderr, "op %4d t%d |", i, g->pk_ops.size() > static_cast<size_t>(i) ? g->pk_ops[i].type : -1);
+          for (int e = 0; e < 14; ++e) {
+            const unsigned long long v = h[static_cast<size_t>(i) * 32 + e];
+            if (v) std::fprintf(stderr, " %7llu", v - t0); else std::fprintf(stderr, "       -");
+            if (e == 2 || e == 4 || e == 10) std::fprintf(stderr, " |");
+          }
+          const unsigned long long c0 = h[static_cast<size_t>(i) * 32 + 14], c1 = h[static_cast<size_t>(i) * 32 + 15];
+          const unsigned long long g0 = h[static_cast<size_t>(i) * 32 + 5], g1 = h[static_cast<size_t>(i) * 32 + 12];
+          if (g1 > g0) std::fprintf(stderr, " | SM clock %.0f MHz", double(c1 - c0) / double(g1 - g0) * 1e3);
+          std::fprintf(stderr, "\n        fine: mma-blocks");
+          for (int e = 16; e < 23; ++e) {
+            const unsigned long long v = h[static_cast<size_t>(i) * 32 + e];
+            if (e == 20) std::fprintf(stderr, " | A-issued setup a_empty");
+            if (v) std::fprintf(stderr, " %7llu", v - t0); else std::fprintf(stderr, "       -");
+          }
+          std::fprintf(stderr, "\n");
+        }
+      }
+    } dump{this, &pr, trace_dev, trace_ops, trace_first, st};
+    Scope sc(this, KC_PK, pr.flops, pr.bytes, st);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(pk_grid); lc.blockDim = dim3(kPkThreads); lc.dynamicSmemBytes = pr.plan.total; lc.stream = st;
+    // co-residency of every CTA (they wait on each other) is guaranteed by construction: pk_grid comes from
+    // cudaOccupancyMaxActiveClusters, and the cooperative attribute makes the driver refuse rather than deadlock
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    lc.attrs = at; lc.numAttrs = pk_coop ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&lc, persistent_kernel, P);
+    if (e != cudaSuccess && pk_coop) {   // cooperative + cluster launches are refused by some drivers: plain launch
+      cudaGetLastError();
+      pk_coop = false;
+      lc.numAttrs = 0;
+      e = cudaLaunchKernelEx(&lc, persistent_kernel, P);
+    }
+    return e;
+  }
+  bool pk_coop = true;
+
+  // rows the widest GEMM of a pass sees
+  bool pk_eligible(int rows) { return tc() && rows <= kPkMaxRows && pk_init(); }
 
   // Latents (B, S, E) fp32 (contiguous or gathered from history slots) -> operand buffer `dst`.
   cudaError_t ingest(const float* src, long long clip_stride, long long slot_stride, const int* slot_list, int B,
@@ -1009,6 +1268,29 @@ class Engine {
     if (mask_kind < 0 || mask_kind > 2 || (mask_kind == 2 && !mask)) return fail(SDVG_ERR_INVALID, "bad mask");
     int r = check_ready(st);
     if (r != SDVG_OK) return r;
+    // small batches: the whole pass is one launch of the persistent kernel (persistent.cuh)
+    if (pk_eligible(B * (Ss > St ? Ss : St))) {
+      const std::vector<long long> key = {1, reinterpret_cast<long long>(src), reinterpret_cast<long long>(tgt),
+                                          reinterpret_cast<long long>(out), reinterpret_cast<long long>(mask),
+                                          reinterpret_cast<long long>(pe_index), B, Ss, St, mask_kind};
+      PkProgram* pr = pk_find(key);
+      if (!pr) {
+        pk_begin();
+        const int rc = forward_enqueue(src, tgt, B, Ss, St, mask_kind, mask, pe_index, out, st);
+        pr = pk_end(key, st);
+        if (rc != SDVG_OK) return rc;
+      }
+      if (pr) {
+        const cudaError_t e = pk_launch(*pr, st);
+        if (e != cudaSuccess) return fail_cuda(e, "persistent forward");
+        return SDVG_OK;
+      }
+    }
+    return forward_enqueue(src, tgt, B, Ss, St, mask_kind, mask, pe_index, out, st);
+  }
+
+  int forward_enqueue(const float* src, const float* tgt, int B, int Ss, int St, int mask_kind, const float* mask,
+                      const int* pe_index, float* out, cudaStream_t st) {
     const bool same = (src == tgt && Ss == St);
     const int E = cfg.latent_dim;
     cudaError_t e = ingest(src, static_cast<long long>(Ss) * E, E, nullptr, B, Ss, 1.0f, lat_s, st);
@@ -1037,6 +1319,27 @@ class Engine {
     int r = check_ready(st);
     if (r != SDVG_OK) return r;
     RolloutKey key{ctx, teacher, pe_index, out, B, C, n_pred, window, flags, scale_in, scale_out};
+    // small batches (the reference's own regime is batch 1, prediction/predict.py:58): every pass of the rollout is
+    // one op program executed by ONE launch of the persistent kernel
+    if (pk_eligible(B * max_S)) {
+      long long si, so;
+      { float f = scale_in; int i; std::memcpy(&i, &f, 4); si = i; f = scale_out; std::memcpy(&i, &f, 4); so = i; }
+      const std::vector<long long> pkey = {2, reinterpret_cast<long long>(ctx), reinterpret_cast<long long>(teacher),
+                                           reinterpret_cast<long long>(pe_index), reinterpret_cast<long long>(out),
+                                           B, C, n_pred, window, flags, si, so};
+      PkProgram* pr = pk_find(pkey);
+      if (!pr) {
+        pk_begin();
+        const int rc = rollout_enqueue(key, st);
+        pr = pk_end(pkey, st);
+        if (rc != SDVG_OK) return rc;
+      }
+      if (pr) {
+        const cudaError_t e = pk_launch(*pr, st);
+        if (e != cudaSuccess) return fail_cuda(e, "persistent rollout");
+        return SDVG_OK;
+      }
+    }
     return rollout_graphed(key, st);
   }
 
@@ -1182,8 +1485,7 @@ class Engine {
         ad.src = s2 >= 0 ? hist + static_cast<size_t>(s2) * E : nullptr; ad.src_clip_stride = hstride;
         ad.fill = 2.0f;  // the SOS frame, if it is the second-to-last token
         ad.clips = B; ad.width = E;
-        Scope sc(this, KC_PACK, 0.0, 12.0 * B * E, st);
-        if ((e = launch_add_rows(ad, num_sms, st)) != cudaSuccess) return fail_cuda(e, "residual add");
+        if ((e = add_rows(ad, st)) != cudaSuccess) return fail_cuda(e, "residual add");
       }
       if (teacher) {
         // export this prediction, then overwrite the slot with the teacher frame

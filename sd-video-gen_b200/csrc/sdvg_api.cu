@@ -263,6 +263,29 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     Engine tmp_eng;
     tmp_eng.num_sms = prop.multiProcessorCount;
     tmp_eng.cfg.precision = precision;
+    if (block_n == 9999) {
+      // the persistent small-batch kernel (persistent.cuh) running a one-op program: M <= 128
+      ActBuf Ab;
+      Ab.p.hi = a_hi; Ab.p.lo = a_lo; Ab.p.rows = Mp; Ab.p.cols = K; Ab.p.ld = Kp;
+      Linear L;
+      L.N = N; L.K = K; L.bias = bias; L.split = split;
+      L.p.hi = w_hi; L.p.lo = w_lo; L.p.rows = N; L.p.cols = K; L.p.ld = Kp;
+      if (err != cudaSuccess || !tmp_eng.pk_eligible(M)) { cleanup(); g_create_error = "sdvg_gemm: persistent kernel unavailable (M > 128 or no cluster launch)"; return SDVG_ERR_UNSUPPORTED; }
+      tmp_eng.pk_begin();
+      int repeat = 1;   // SDVG_PK_REPEAT=n: the same op n times in one program (per-op cost in steady state)
+      if (const char* rv = std::getenv("SDVG_PK_REPEAT")) repeat = std::atoi(rv) > 0 ? std::atoi(rv) : 1;
+      for (int r = 0; r < repeat; ++r) tmp_eng.gemm(Ab, L, M, e, st);
+      Engine::PkProgram* pr = tmp_eng.pk_end({9999}, st);
+      if (!pr) { cleanup(); g_create_error = "sdvg_gemm: persistent program rejected"; return SDVG_ERR_UNSUPPORTED; }
+      cudaEventRecord(ev0, st);
+      for (int i = 0; i < iters && err == cudaSuccess; ++i) err = tmp_eng.pk_launch(*pr, st);
+      cudaEventRecord(ev1, st);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+      if (err != cudaSuccess) { g_create_error = std::string("sdvg_gemm (persistent): ") + cudaGetErrorString(err); rc = SDVG_ERR_CUDA; }
+      else if (ms) { float t = 0.f; cudaEventElapsedTime(&t, ev0, ev1); *ms = t / iters; }
+      cleanup();
+      return rc;
+    }
     // block_n >= 1000 (tests): split-K factor block_n / 1000 with tile width block_n % 1000 (one-CTA kernel, M <= 128)
     int force_ks = 1;
     if (block_n >= 1000) { force_ks = block_n / 1000; block_n %= 1000; }
