@@ -48,6 +48,8 @@ def parse():
     p.add_argument("--precision", default="mixed", choices=["fp32_simt", "fp32", "fp16", "bf16", "mixed"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-steps", type=int, default=2)
+    p.add_argument("--no-extras", action="store_true", help="skip the `extra` block (the other BASELINE configs)")
+    p.add_argument("--extra-steps", type=int, default=3)
     p.add_argument("--workload", default="rollout", choices=["rollout", "train"],
                    help="train: the data-parallel training step of BASELINE configs[4] (same as bench_train.py)")
     return p.parse_known_args()[0]
@@ -160,6 +162,168 @@ def run_reference_arm(a, cfg, E):
     print(json.dumps(line), flush=True)
 
 
+def read_traffic(a, B):
+    """roofline.traffic = dram bytes per launch of the dominant GEMM instantiation from an `ncu --set full` capture of
+    THIS workload (profiles/r2_traffic.json).  The file records the commit it was measured at; when git is available
+    and that commit is not an ancestor of HEAD, or the kernel sources changed since, the number is dropped (a static
+    file must not silently go stale)."""
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not (os.path.exists(tpath) and a.config == "1_15_kitti_L1_64" and B == 1024 and a.precision in ("mixed", "fp16")):
+        return None, None
+    tj = json.load(open(tpath))
+    note = (f'{tj["kernel"]}; algorithmic {tj["algorithmic_bytes_per_launch"]} B; {tj["source"]}; captured at commit '
+            f'{tj.get("git_head", "?")[:12]}')
+    try:
+        import hashlib
+        h = hashlib.sha256()
+        for f in tj.get("kernel_sources", []):
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        if tj.get("kernel_sources_sha256") and h.hexdigest() != tj["kernel_sources_sha256"]:
+            return None, note + " - STALE: the kernel sources changed since the capture"
+        if os.path.isdir(os.path.join(ROOT, ".git")) and tj.get("git_head"):
+            r = subprocess.run(["git", "-C", ROOT, "merge-base", "--is-ancestor", tj["git_head"], "HEAD"], capture_output=True)
+            if r.returncode != 0:
+                return None, note + " - STALE: not an ancestor of HEAD"
+    except OSError:
+        pass
+    return tj["traffic_bytes_per_launch"], note
+
+
+def run_extras(a, model_c2, world, rank, local, dev):
+    """Short, clock-sampled sub-benches of every other BASELINE.json config, in the same JSON line (`extra`):
+    C1 (configs[0], B = 8, windows 5 and 10; per-kernel path and the persistent one-launch path), C2 in fp32 mode, strong
+    scaling of configs[1] (1024 clips TOTAL over N GPUs), C3, C4 (the "wide" target: fraction of the bf16 tensor peak on
+    executed FLOPs) and the C5 training step (with the gradient all-reduce at N > 1).  A few steps each."""
+    import torch
+    import torch.distributed as dist
+    import sdvg_b200
+    pk = peaks()
+    K, WARM = max(2, a.extra_steps), 2
+    out = {}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(model, name, cfg_name, B, W, precision, C=10, P=10, gather=True, note=None):
+        cfg = sdvg_b200.CONFIGS[cfg_name]
+        E = sdvg_b200.latent_dim(cfg["frame_size"])
+        model.set_precision(precision)
+        model.reserve(max_clips=B, max_tokens=min(W, C + P), max_history=C + P)
+        ctx = torch.randn(B, C, E, generator=torch.Generator().manual_seed(77 + rank)).to(dev)
+        pe = sdvg_b200.pe_index_for(rank * B, (rank + 1) * B, dev)
+        res = torch.empty(B, P, E, device=dev)
+        gathered = torch.empty(world * B, P, E, device=dev) if (world > 1 and gather) else None
+
+        def step():
+            sdvg_b200.rollout(model, ctx, P, W, pe_index=pe, out=res)
+            if gathered is not None:
+                dist.all_gather_into_tensor(gathered, res)
+        for _ in range(WARM + 1):
+            step()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = model.launch_count()
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item()) / K
+        launches = (model.launch_count() - n0) // K
+        clocks = sampler.stop() if rank == 0 else None
+        model.timing(True)
+        model.timing_read()
+        sdvg_b200.rollout(model, ctx, P, W, pe_index=pe, out=res)
+        prof = model.timing_read()
+        model.timing(False)
+        flops = prof["gemm_tc"]["flops"] + prof["persistent"]["flops"]
+        gemm_ms = prof["gemm_tc"]["ms"]
+        n_param = sum(p.numel() for k, p in model.named_parameters() if p.dim() == 2)
+        wbytes = prof["persistent"]["bytes"] / P if prof["persistent"]["launches"] else n_param * (4.0 if precision == "fp32" else 2.0)
+        r = {"workload": f"{cfg_name} rollout: {B} clips/GPU x {world} GPU, {C} ctx -> {P} pred, window {W}, {precision}",
+             "frames_per_s": world * B * P / (ms * 1e-3), "ms_per_rollout": ms, "ms_per_pass": ms / P, "steps": K, "warmup": WARM + 1,
+             "launches_per_rollout": int(launches), "clocks": clocks,
+             "step_tflops_executed": flops / (ms * 1e-3) / 1e12,
+             "frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / pk["tflops"],
+             "frac_of_burst_bf16_peak": flops / (ms * 1e-3) / 1e12 / pk["burst"] if pk.get("burst") else None,
+             "gemm_class_tflops": (prof["gemm_tc"]["flops"] / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else None,
+             "weight_stream_gbs": wbytes / (ms / P * 1e-3) / 1e9, "frac_of_hbm_peak": wbytes / (ms / P * 1e-3) / 1e9 / pk["hbm"],
+             "classes_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}}
+        if note:
+            r["note"] = note
+        out[name] = r if rank == 0 else None
+
+    def fresh(cfg_name, B, W, precision, env_pk=None):
+        cfg = sdvg_b200.CONFIGS[cfg_name]
+        if env_pk is not None:
+            os.environ["SDVG_PK"] = env_pk
+        torch.manual_seed(0)
+        m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"],
+                                  cfg["dropout_p"], frame_size=cfg["frame_size"], precision=precision, max_clips=B,
+                                  max_tokens=min(W, 20), max_history=20)
+        return m.eval().to(dev)
+
+    hbm_note = ("HBM-bound (M = clips x window rows << the 213 FLOP/B ridge): the roofline is the weight-plane bytes one pass "
+                "streams over the pass time against the measured HBM bandwidth")
+    # ---- C2 architecture (the headline model object is reused: same seeded weights)
+    measure(model_c2, "c2_fp32", "1_15_kitti_L1_64", a.batch, a.window, "fp32",
+            note="strict fp32-parity mode (split fp16x2 operands, 3 MMAs per product; <= 1e-4 free-running)")
+    if world > 1 and a.batch % world == 0:
+        measure(model_c2, "c2_strong_scaling", "1_15_kitti_L1_64", a.batch // world, a.window, a.precision,
+                note=f"strong scaling of configs[1]: {a.batch} clips TOTAL over {world} GPUs, final all-gather inside the step")
+    # ---- C1: BASELINE configs[0], B = 8 (same architecture as C2), per-kernel launch chain
+    measure(model_c2, "c1_w5", "1_17_ball_complex_L1_64", 8, 5, a.precision, gather=False, note=hbm_note)
+    measure(model_c2, "c1_w10", "1_17_ball_complex_L1_64", 8, 10, a.precision, gather=False, note=hbm_note)
+    model_c2._free()
+    # ---- C1 through the persistent one-launch kernel (SDVG_PK=1, read when the engine is created)
+    prev = os.environ.get("SDVG_PK")
+    os.environ["SDVG_PK"] = "1"
+    try:
+        measure(model_c2, "c1_w5_persistent", "1_17_ball_complex_L1_64", 8, 5, a.precision, gather=False,
+                note=hbm_note + "; the whole rollout is ONE launch of sdvg::persistent_kernel")
+        measure(model_c2, "c1_w5_persistent_fp32", "1_17_ball_complex_L1_64", 8, 5, "fp32", gather=False,
+                note="persistent kernel, fp32-parity mode (the case where it beats the launch chain)")
+        measure(model_c2, "c1_b1_persistent_fp32", "1_17_ball_complex_L1_64", 1, 5, "fp32", gather=False,
+                note="batch 1 - the reference's own inference regime (prediction/predict.py:58)")
+    finally:
+        model_c2._free()
+        if prev is None:
+            os.environ.pop("SDVG_PK", None)
+        else:
+            os.environ["SDVG_PK"] = prev
+    measure(model_c2, "c1_b1_fp32", "1_17_ball_complex_L1_64", 1, 5, "fp32", gather=False, note="batch 1, per-kernel launch chain")
+    model_c2._free()
+    torch.cuda.empty_cache()
+    # ---- C3 / C4
+    for name, cfg_name in (("c3", "11_27_ucf_final"), ("c4", "11_20_wallpushups_dim_2048")):
+        m = fresh(cfg_name, a.batch, a.window, a.precision)
+        measure(m, name, cfg_name, a.batch, a.window, a.precision,
+                note="north_star target: >= 50 % of the bf16 tensor peak on the wide config - fractions are on EXECUTED FLOPs "
+                     "against the measured sustained and burst cuBLAS peaks" if name == "c4" else None)
+        m._free()
+        del m
+        torch.cuda.empty_cache()
+    # ---- C5: the data-parallel training step (gradient all-reduce at N > 1)
+    import bench_train
+    ta = bench_train.parse(["--gpus", str(world), "--steps", str(max(5, K)), "--warmup", "3", "--no-cpu-baseline"])
+    tr = bench_train.measure(ta, quick=True)
+    if rank == 0 and tr is not None:
+        out["c5_train_step"] = {"workload": tr["config"]["workload"], "clips_per_s": tr["value"], "ms_per_step": tr["ms_per_step"],
+                                "n_gpus": tr["n_gpus"], "launches_per_step": tr["roofline"]["launches_per_step"],
+                                "hbm_gbs": tr["roofline"]["achieved"], "frac_of_hbm_peak": tr["roofline"]["frac"],
+                                "clocks": tr["clocks"], "classes_ms": tr["roofline"]["classes_ms"],
+                                "note": "weak scaling, 16 clips/GPU; at N > 1 the NCCL gradient all-reduce is inside the step"}
+    return out if rank == 0 else None
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(a, cfg, E):
     import torch
@@ -243,11 +407,7 @@ def run_ours(a, cfg, E):
     prof = model.timing_read()
     model.timing(False)
     pk = peaks()
-    traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
-    if os.path.exists(tpath) and a.config == "1_15_kitti_L1_64" and B == 1024 and a.precision in ("mixed", "fp16"):
-        tj = json.load(open(tpath))      # dram__bytes_read+write per launch of the dominant GEMM instantiation (ncu --set full)
-        traffic, traffic_note = tj["traffic_bytes_per_launch"], f'{tj["kernel"]}; algorithmic {tj["algorithmic_bytes_per_launch"]} B; {tj["source"]}'
+    traffic, traffic_note = read_traffic(a, B)
     cls = "gemm_tc" if prof["gemm_tc"]["launches"] else "gemm_simt"
     gk = prof[cls]
     achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12 if gk["ms"] > 0 else 0.0
@@ -261,11 +421,20 @@ def run_ours(a, cfg, E):
                 "classes_gbs": {k: (round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None)
                                 for k, v in prof.items() if k in ("attention", "layernorm", "pack")},
                 "hbm_peak_gbs": pk["hbm"]}
-    # whole-step view: reference-equivalent FLOPs (F_ref) over the device-timed step
+    # whole-step view on EXECUTED FLOPs (2MNK of the GEMMs the step really launches: the exact caches and the last-layer
+    # pruning skip ~10 % of the reference's work, and skipped work is not counted - SURVEY.md 8d) over the device-timed
+    # step, against both peaks; the reference-equivalent figure (F_ref) is kept beside it, labelled as such
+    roofline["step_tflops_executed"] = gk["flops"] / (ms / a.steps * 1e-3) / 1e12
+    roofline["step_frac_of_sustained"] = roofline["step_tflops_executed"] / pk["tflops"]
+    roofline["step_frac_of_burst"] = roofline["step_tflops_executed"] / pk["burst"] if pk.get("burst") else None
     f_ref = flops_per_clip_step(cfg, E, min(W, C)) * B * P
     roofline["step_tflops_ref_equiv"] = f_ref / (ms / a.steps * 1e-3) / 1e12
-    roofline["step_frac_of_peak"] = roofline["step_tflops_ref_equiv"] / pk["tflops"]
+    roofline["executed_over_ref_flops"] = gk["flops"] / f_ref if f_ref else None
 
+    extra = None
+    if not a.no_extras:
+        del host
+        extra = run_extras(a, model, world, rank, local, dev)
     line = None
     if rank == 0:
         line = {
@@ -281,6 +450,10 @@ def run_ours(a, cfg, E):
                        "l2": "no flush: per-step working set (>=0.9 GB weights + activations) exceeds the 126 MB L2"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         }
+        line["e2e"]["note"] = ("each rank copies its clips in from pinned host memory and its predictions back out; at N > 1 the "
+                               "device-side all-gather of `value` is not part of this leg (every rank returns its own shard to its host)")
+        if extra is not None:
+            line["extra"] = extra
         if world == 1 and not a.no_cpu_baseline:
             import torch as _t
             cores = os.cpu_count() or 1

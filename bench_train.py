@@ -66,7 +66,14 @@ def cpu_step(cfg, E, batch, steps):
 
 
 def main(argv=None):
-    a = parse(argv)
+    out = measure(parse(argv))
+    if out is not None:
+        print(json.dumps(out))
+
+
+def measure(a, quick=False):
+    """Runs the benchmark and returns the JSON line as a dict on rank 0 (None elsewhere).  `quick` (bench.py's `extra`
+    block): no end-to-end leg, no CPU baseline, the process group of the caller is reused."""
     import torch
     import sdvg_b200
     cfg = sdvg_b200.CONFIGS[a.config]
@@ -87,18 +94,18 @@ def main(argv=None):
         steps = max(1, min(a.steps, 5))
         dt = cpu_step(cfg, E, a.batch, steps)
         v = a.batch / dt
-        print(json.dumps({**base, "impl": "reference", "value": v, "n_gpus": 0, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
-                          "dtype": "f32", "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
-                                                           "sample": f"{steps} full steps of {a.batch} clips"},
-                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+        return {**base, "impl": "reference", "value": v, "n_gpus": 0, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
+                "dtype": "f32", "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port",
+                                                 "sample": f"{steps} full steps of {a.batch} clips"},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)      # same weights on every rank (and as the CPU arm: the module initialises like the reference)
     m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"],
                               cfg["dropout_p"], frame_size=cfg["frame_size"], precision=a.precision)
@@ -149,7 +156,7 @@ def main(argv=None):
         x = host[i % 4].to(dev, non_blocking=True)
         loss_host.copy_(tr.step(x, pe_index=pe), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    ms_e2e = timed(e2e_step, a.steps)
+    ms_e2e = ms if quick else timed(e2e_step, a.steps)
 
     clocks = sampler.stop() if sampler else None
     # per-kernel-class device time of one step (instrumented pass, outside the timed regions)
@@ -158,8 +165,10 @@ def main(argv=None):
     classes = {k: round(v["ms"], 3) for k, v in m.timing_read().items()}
     gemm_flops = None
     m.timing(False)
+    del tr
+    m._free()
     if rank != 0:
-        return
+        return None
     P = param_count(cfg, E)
     split = a.precision == "fp32"
     plane = 4.0 if split else 2.0
@@ -180,13 +189,13 @@ def main(argv=None):
            "roofline": {"bound": "hbm", "achieved": bytes_step / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": bytes_step / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": src,
                         "algorithmic_bytes_per_step": bytes_step, "launches_per_step": int(launches), "classes_ms": classes}}
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and not quick:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         dt = cpu_step(cfg, E, a.batch, 2)
         out["cpu_baseline"] = {"value": a.batch / dt, "unit": unit, "cores": cores, "kind": "port",
                                "sample": f"2 full steps of {a.batch} clips (oracle/train.py)", "ms_per_step": dt * 1e3}
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":

@@ -190,6 +190,19 @@ int sdvg_train_backward(sdvg_handle* h, const float* src, const float* tgt, cons
                         int32_t S_tgt, const sdvg_loss_config* loss, const int32_t* pe_index, float* losses, int32_t part,
                         void* stream);
 
+/* The two halves of sdvg_train_backward around a loss that lives in the caller - the torch.autograd bridge that lets
+ * the reference's loop body run unmodified: `pred = model(new_batch, y_input, tgt_mask)` (trainers/trainer.py:141),
+ * `loss = loss_fn(pred[-P:], ...)` (:145, the reference's own torch criterion), `opt.zero_grad(); loss.backward();
+ * opt.step()` (:163-165) with `optim.Adam(model.parameters())` (:365).
+ *   sdvg_train_forward: Transformer.forward in train() mode - activations saved, dropout as set by
+ *     sdvg_train_set_dropout, causal target mask; pred (S_tgt, B, E) device fp32 is written.  src / tgt must stay
+ *     alive until the backward call (the embedding weight gradient reads them).
+ *   sdvg_train_backward_from: dpred (S_tgt, B, E) device fp32 = dL/dpred from the caller's autograd graph; the
+ *     parameter gradients land in the flat vector of sdvg_train_gradients exactly as with sdvg_train_backward. */
+int sdvg_train_forward(sdvg_handle* h, const float* src, const float* tgt, int32_t B, int32_t S_src, int32_t S_tgt,
+                       const int32_t* pe_index, float* pred, void* stream);
+int sdvg_train_backward_from(sdvg_handle* h, const float* dpred, void* stream);
+
 /* The flat gradient vector (device fp32, `count` elements) and the offset of the decoder-side bucket.  This is the
  * buffer a data-parallel trainer hands to ncclAllReduce (torch.distributed.all_reduce on a tensor view of it). */
 int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t* decoder_offset);

@@ -16,7 +16,7 @@ SYMBOLS = (
     "sdvg_num_weights", "sdvg_weight_key", "sdvg_finalize_weights", "sdvg_forward", "sdvg_rollout",
     "sdvg_timing_enable", "sdvg_timing_read", "sdvg_launch_count", "sdvg_gemm", "sdvg_criterion",
     "sdvg_train_backward", "sdvg_train_gradients", "sdvg_train_set_ready_callback", "sdvg_train_set_dropout", "sdvg_param_range", "sdvg_train_prediction", "sdvg_train_adam_step", "sdvg_train_adam_step_range",
-    "sdvg_get_weight",
+    "sdvg_get_weight", "sdvg_train_forward", "sdvg_train_backward_from",
 )
 
 
@@ -47,7 +47,8 @@ def load(build_if_missing=True):
         try:
             from . import build as _build
             _build.build()
-        except Exception:
+        except FileNotFoundError:
+            # no nvcc on this machine: use the shipped library if there is one (compile errors are NOT swallowed)
             if not os.path.exists(LIB_PATH):
                 raise
     if not os.path.exists(LIB_PATH):
@@ -85,6 +86,8 @@ def load(build_if_missing=True):
     lib.sdvg_train_adam_step.argtypes = [vp, f32, f32, f32, f32, f32, vp]
     lib.sdvg_train_adam_step_range.argtypes = [vp, f32, f32, f32, f32, f32, C.c_int64, C.c_int64, i32, vp]
     lib.sdvg_get_weight.argtypes = [vp, C.c_char_p, vp, vp]
+    lib.sdvg_train_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.sdvg_train_backward_from.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 

@@ -2,6 +2,7 @@
 from . import _lib
 from .config import CONFIGS, latent_dim, parse_config_args
 from .dist import pe_index_for, rollout_sharded, shard_bounds
+from .latent_cache import load_latent_clips, load_latent_frames, save_latent_frames
 from .positional_encoding import PositionalEncoding
 from .predict import (LATENT_SCALE, SOS_VALUE, HostRollout, predict, predict_diff, predict_future, rollout,
                       rollout_from_host)
@@ -13,7 +14,8 @@ __all__ = ["Transformer", "TransformerFuture", "Identity", "PositionalEncoding",
            "predict_future", "rollout", "rollout_from_host", "HostRollout",
            "rollout_sharded", "shard_bounds", "pe_index_for", "CONFIGS", "latent_dim", "parse_config_args",
            "LATENT_SCALE", "SOS_VALUE", "gemm", "build_library", "criterion", "gradient_difference_loss", "BiPatchNCE",
-           "loss_terms", "validation_step", "AdamTrainer", "allreduce_buckets"]
+           "loss_terms", "validation_step", "AdamTrainer", "allreduce_buckets", "load_latent_clips", "load_latent_frames",
+           "save_latent_frames"]
 
 
 def build_library(force=False, verbose=False):

@@ -22,17 +22,31 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """Compile into a temporary file and rename it over libsdvg.so, under a file lock: in a torchrun launch every rank
+    calls this, and nobody may dlopen a half-written library."""
+    import fcntl
     if not force and not stale():
         return LIB
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC,-O2", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB, os.path.join(CSRC, "sdvg_api.cu")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libsdvg.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():      # another process built it while we waited
+                return LIB
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                   "-shared", "-Xcompiler", "-fPIC,-O2", "-Xptxas", "-v" if verbose else "-O3",
+                   "-o", tmp, os.path.join(CSRC, "sdvg_api.cu")]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed building libsdvg.so")
+            os.replace(tmp, LIB)
+            if verbose:
+                sys.stderr.write(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

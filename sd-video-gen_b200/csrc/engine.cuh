@@ -132,7 +132,9 @@ class Engine {
   // ---- persistent small-batch path (persistent.cuh): while pk_rec is set, gemm() / layernorm() / attention() /
   // pack() / add_rows() append ops to pk_ops instead of launching, so run_model() and rollout_enqueue() are the one
   // description of the model for both the per-kernel path and the one-launch path
-  bool use_pk = true;          // SDVG_PK=0 disables
+  bool use_pk = false;         // SDVG_PK=1 enables: measured on B200 (profiles/README.md, round 2) a pass costs ~8 us per
+                               // dependent GEMM stage inside the kernel vs ~7 us per kernel boundary of the launch chain, so the
+                               // one-launch path only wins in fp32 (split) mode at window 5; it stays selectable and tested
   bool pk_rec = false;
   bool pk_bad = false;         // an op the persistent kernel cannot run was recorded: fall back to per-kernel launches
   std::vector<PkOp> pk_ops;
@@ -471,6 +473,13 @@ class Engine {
     if (ndim != static_cast<int>(s.shape.size())) return fail(SDVG_ERR_INVALID, "'%s': rank %d, expected %zu", key, ndim, s.shape.size());
     for (int i = 0; i < ndim; ++i)
       if (shape[i] != s.shape[i]) return fail(SDVG_ERR_INVALID, "'%s': dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)s.shape[i]);
+    // The copy runs on the legacy stream, which is not ordered against the library's non-blocking streams (graph
+    // replays, the training side stream) nor torch's: a weight push begins with one device-wide synchronisation, so no
+    // in-flight kernel still reads the arena (biases, LayerNorm parameters, the PE table are read from it directly).
+    if (finalized) {
+      cudaError_t es = cudaDeviceSynchronize();
+      if (es != cudaSuccess) return fail_cuda(es, "synchronise before weight push");
+    }
     cudaError_t e = cudaMemcpy(s.dev, data, s.count * sizeof(float), cudaMemcpyDefault);
     if (e != cudaSuccess) return fail_cuda(e, "weight copy");
     s.set = true;

@@ -895,10 +895,15 @@ persistent_kernel(const __grid_constant__ PkParams P) {
         for (int i = wt; i < static_cast<int>(sizeof(PkOp) / 4); i += 128) sdst[i] = __ldg(gsrc + i);
       }
       const PkOp* op = op_s;
-      // everything this op reads from global memory was written before the previous op's barrier
-      if (wt == 0) { PK_TRACE(5); if (P.trace && static_cast<int>(blockIdx.x) == P.trace_cta) P.trace[static_cast<size_t>(oi) * 32 + 14] = clock64(); pkx::grid_wait(ctr, static_cast<unsigned>(oi) * n_cta); PK_TRACE(6); }
       pkx::worker_bar();
+      // everything this op reads from global memory was written before the previous op's barrier; the op's own set-up
+      // (descriptor decode, address tables) runs before the wait, while the slowest CTA is still arriving
+      auto wait_previous_op = [&]() {
+        if (wt == 0) { PK_TRACE(5); if (P.trace && static_cast<int>(blockIdx.x) == P.trace_cta) P.trace[static_cast<size_t>(oi) * 32 + 14] = clock64(); pkx::grid_wait(ctr, static_cast<unsigned>(oi) * n_cta); PK_TRACE(6); }
+        pkx::worker_bar();
+      };
       const int type = op->type;
+      if (type != PK_GEMM) wait_previous_op();
       if (type == PK_GEMM) {
         const PkGemm& g = op->u.g;
         const int M = g.M, N = g.N, T = g.T, MT = g.MT, n_tiles = g.n_tiles, lda = g.lda;
@@ -927,6 +932,7 @@ persistent_kernel(const __grid_constant__ PkParams P) {
         const bool lean = e.row_map == 0 && e.res_clip_rows == 0 && !e.pe && !e.gate && !e.drop_thr && !e.alpha_dev;
         const int groups = (M + kPkGroup - 1) / kPkGroup;
         const int rpt_sel = T <= 32 ? 4 : (T <= 64 ? 8 : 16);
+        wait_previous_op();
         for (int t = cluster; t < n_tiles; t += n_clusters) {
           if (have_k) {
             // this CTA's K slab of the activations -> swizzled operand stages, every block in flight at once.  Stages are

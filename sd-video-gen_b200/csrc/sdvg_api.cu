@@ -139,6 +139,30 @@ int sdvg_train_backward(sdvg_handle* h, const float* src, const float* tgt, cons
   }
 }
 
+int sdvg_train_forward(sdvg_handle* h, const float* src, const float* tgt, int32_t B, int32_t S_src, int32_t S_tgt,
+                       const int32_t* pe_index, float* pred, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  sdvg::Trainer* t = trainer_of(h);
+  if (!t) return h->eng.fail(SDVG_ERR_INVALID, "out of host memory");
+  try {
+    return t->forward_only(src, tgt, B, S_src, S_tgt, pe_index, pred, static_cast<cudaStream_t>(stream));
+  } catch (const std::exception& ex) {
+    return h->eng.fail(SDVG_ERR_INVALID, "exception: %s", ex.what());
+  }
+}
+
+int sdvg_train_backward_from(sdvg_handle* h, const float* dpred, void* stream) {
+  if (!h) return SDVG_ERR_INVALID;
+  cudaSetDevice(h->eng.cfg.device);
+  if (!h->trainer) return h->eng.fail(SDVG_ERR_STATE, "backward without a saved training forward pass");
+  try {
+    return h->trainer->backward_from(dpred, static_cast<cudaStream_t>(stream));
+  } catch (const std::exception& ex) {
+    return h->eng.fail(SDVG_ERR_INVALID, "exception: %s", ex.what());
+  }
+}
+
 int sdvg_train_gradients(sdvg_handle* h, float** grads, int64_t* count, int64_t* decoder_offset) {
   if (!h) return SDVG_ERR_INVALID;
   cudaSetDevice(h->eng.cfg.device);

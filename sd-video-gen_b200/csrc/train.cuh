@@ -572,6 +572,16 @@ __global__ void __launch_bounds__(256) loss_grad_nce_kernel(const __grid_constan
   if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(a.amax_bits, __float_as_uint(amax));
 }
 
+// max |x| of an upstream gradient handed in by the caller (torch.autograd bridge, sdvg_train_backward_from): feeds
+// the same power-of-two loss scale as the fused criterion gradient kernels above.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n, unsigned int* amax_bits) {
+  float amax = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) amax = fmaxf(amax, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f && amax < INFINITY) atomicMax(amax_bits, __float_as_uint(amax));
+}
+
 // scale[0] = S = 2^k with S * amax in [32, 64), scale[1] = 1 / S; resets amax for the next step.
 __global__ void loss_scale_kernel(unsigned int* amax_bits, float* scale) {
   pdl_wait();

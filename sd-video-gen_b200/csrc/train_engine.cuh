@@ -8,9 +8,10 @@
 //     pack_t(x)   -> x^T planes [K][Mp]
 //     dW = dy^T x      tensor-core GEMM, epilogue multiplies by 1/S, writes the fp32 gradient in place
 //     dx = dy W        tensor-core GEMM against the W^T planes, epilogue adds the residual-path gradient
-// S is the device-side power-of-two loss scale (train.cuh).  Dropout is the identity here: the reference trains
-// with DROPOUT_P 0.1 and torch's Philox stream, which cannot be reproduced bit-for-bit, so parity is defined (and
-// tested) for dropout_p = 0 as SURVEY.md section 8(e) prescribes.
+// S is the device-side power-of-two loss scale (train.cuh).  Dropout (model.train(), DROPOUT_P of the config) is
+// applied at nn.Transformer's sites with the library's counter-based masks (common.cuh: drop_hash) - in the forward
+// epilogues / the training attention kernel, and regenerated in the backward pass; torch's Philox stream cannot be
+// reproduced by another implementation, so parity is tested under the same masks (the test-suite's CPU checker restates the hash) and for p = 0.
 #pragma once
 #include "engine.cuh"
 #include "loss.cuh"
@@ -670,6 +671,50 @@ class Trainer {
       cudaError_t e = backward_encoder(st);
       if (e != cudaSuccess) return g.fail_cuda(e, "encoder backward");
     }
+    return SDVG_OK;
+  }
+
+  // ------------------------------------------------------------------ torch.autograd bridge
+  // The reference's loop body is `pred = model(...)`, `loss = loss_fn(...)`, `loss.backward()`, `opt.step()`
+  // (trainers/trainer.py:141-165) with torch's own criterion and optimiser.  These two calls are the halves of
+  // forward_backward() around a loss that lives in the caller: the training-mode forward pass (activations saved,
+  // dropout at nn.Transformer's sites) and the backward pass from the upstream gradient dL/dpred.
+  int forward_only(const float* src, const float* tgt, int B, int Ss, int St, const int* pe_index, float* pred_out, cudaStream_t st) {
+    int rc = init();
+    if (rc != SDVG_OK) return rc;
+    if (!src || !tgt || !pred_out) return g.fail(SDVG_ERR_INVALID, "null tensor");
+    if (B <= 0 || Ss <= 0 || St <= 0 || B > g.cfg.max_clips || Ss > g.cfg.max_tokens || St > g.cfg.max_tokens)
+      return g.fail(SDVG_ERR_INVALID, "B=%d S_src=%d S_tgt=%d exceed the handle's limits (%d clips, %d tokens)", B, Ss, St,
+                    g.cfg.max_clips, g.cfg.max_tokens);
+    if (!pe_index && B > 64) return g.fail(SDVG_ERR_BATCH, "B=%d > 64 without pe_index (models/positional_encoding.py:35)", B);
+    if ((rc = g.check_ready(st)) != SDVG_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    if (wt_stale) e = repack_weights(false, st);
+    if (e == cudaSuccess) e = forward(src, tgt, B, Ss, St, pe_index ? pe_index : g.pe_mod64, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(pred_out, pred, static_cast<size_t>(St) * B * g.cfg.latent_dim * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return g.fail_cuda(e, "training forward");
+    return SDVG_OK;
+  }
+
+  int backward_from(const float* dpred_in, cudaStream_t st) {
+    if (!ready || Bc == 0) return g.fail(SDVG_ERR_STATE, "backward without a saved training forward pass");
+    if (!dpred_in) return g.fail(SDVG_ERR_INVALID, "null gradient");
+    const long long n = static_cast<long long>(Stc) * Bc * g.cfg.latent_dim;
+    cudaError_t e = cudaMemcpyAsync(dpred, dpred_in, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) {
+      Engine::Scope sc(&g, KC_PACK, 0.0, 4.0 * n, st);
+      long long blocks = (n + 255) / 256;
+      if (blocks > g.num_sms * 4) blocks = g.num_sms * 4;
+      e = launch_kernel(absmax_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, static_cast<const float*>(dpred), n, amax);
+    }
+    if (e == cudaSuccess) {
+      Engine::Scope sc(&g, KC_PACK, 0.0, 16.0, st);
+      e = launch_kernel(loss_scale_kernel, dim3(1), dim3(1), 0, st, amax, scale);
+    }
+    if (e == cudaSuccess) e = backward_decoder(st);
+    if (e == cudaSuccess) e = backward_encoder(st);
+    if (e != cudaSuccess) return g.fail_cuda(e, "backward from upstream gradient");
     return SDVG_OK;
   }
 

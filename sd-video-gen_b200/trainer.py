@@ -257,17 +257,6 @@ class AdamTrainer:
 
     def pull_weights(self):
         """Copy the trained parameters back into the module (``model.state_dict()`` for torch.save, :294)."""
-        self.model._pending_pull = None
-        device = next(self.model.parameters()).device
-        h = self._handle(device)
-        lib = _lib.load()
-        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        with torch.no_grad():
-            for k, p in self.model.named_parameters():
-                if k == "learned_tgt":
-                    continue
-                buf = torch.empty_like(p, dtype=torch.float32).contiguous()
-                _lib.check(lib.sdvg_get_weight(h, k.encode(), C.c_void_p(buf.data_ptr()), stream), h)
-                p.copy_(buf)
-        self.model._weights_stamp = self.model._stamp()     # the engine already holds exactly these values
+        self.model._pending_pull = self
+        self.model._sync_trained_weights()
         return self.model

@@ -20,6 +20,54 @@ from .config import latent_dim
 from .positional_encoding import PositionalEncoding
 
 
+class _TrainForward(torch.autograd.Function):
+    """``pred = model(src, tgt, mask)`` in train() mode as a node of torch's autograd graph: forward = libsdvg's
+    training forward pass (activations saved in the engine), backward = libsdvg's backward pass from dL/dpred; the
+    parameter gradients come back as tensors, so ``loss.backward()`` fills ``p.grad`` and ``optim.Adam(model.parameters())``
+    steps exactly as in the reference's loop (trainers/trainer.py:141-165,365)."""
+
+    @staticmethod
+    def forward(ctx, model, src, tgt, pe_index, *params):
+        lib = _lib.load()
+        device = src.device
+        B, Ss, St = src.size(0), src.size(1), tgt.size(1)
+        h = model.engine(device)
+        _lib.check(lib.sdvg_train_set_dropout(h, float(model.dropout_p), int(getattr(model, "dropout_seed", 0))), h)
+        pred = torch.empty(St, B, model.latent_dim, device=device, dtype=torch.float32)
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.sdvg_train_forward(h, src.data_ptr(), tgt.data_ptr(), B, Ss, St,
+                                          None if pe_index is None else pe_index.data_ptr(), pred.data_ptr(), stream), h)
+        ctx.model, ctx.handle, ctx.keep = model, h, (src, tgt, pe_index)     # src / tgt are read again by the backward pass
+        ctx.keys = [k for k, _ in model.named_parameters() if k != "learned_tgt"]
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        lib = _lib.load()
+        model, h = ctx.model, ctx.handle
+        if model._handle is not h:
+            raise RuntimeError("the engine was rebuilt between forward and backward (reserve / set_precision / .to())")
+        device = dpred.device
+        dpred = dpred.detach().float().contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.sdvg_train_backward_from(h, dpred.data_ptr(), stream), h)
+        ptr, n, off = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(lib.sdvg_train_gradients(h, C.byref(ptr), C.byref(n), C.byref(off)), h)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4", "data": (int(ptr.value), False),
+                                        "version": 3, "strides": None}
+        flat = torch.as_tensor(_Arr(), device=device)
+        grads = []
+        sd = dict(model.named_parameters())
+        for k in ctx.keys:
+            o, c = C.c_int64(), C.c_int64()
+            _lib.check(lib.sdvg_param_range(h, k.encode(), C.byref(o), C.byref(c)))
+            # a copy: the flat vector is library memory that the next backward pass overwrites
+            grads.append(flat[o.value:o.value + c.value].view(sd[k].shape).clone())
+        return (None, None, None, None, *grads)
+
+
 class Transformer(nn.Module):
     def __init__(self, num_tokens=0, dim_model=256, num_heads=8, num_encoder_layers=6, num_decoder_layers=6,
                  dropout_p=0.1, *, frame_size=None, precision="fp32", max_clips=64, max_tokens=16, max_history=32):
@@ -62,11 +110,35 @@ class Transformer(nn.Module):
     def state_dict(self, *args, **kwargs):
         """nn.Module.state_dict; after AdamTrainer steps the trained values live in the engine, so they are copied back
         into the parameters first (torch.save(model.state_dict()), trainers/trainer.py:294, sees the trained weights)."""
-        pending = getattr(self, "_pending_pull", None)
-        if pending is not None:
-            self._pending_pull = None
-            pending.pull_weights()
+        self._sync_trained_weights()
         return super().state_dict(*args, **kwargs)
+
+    def _sync_trained_weights(self):
+        """If an AdamTrainer (or loss.backward() + optimizer bridge) left newer weights in the engine than in the
+        module's parameters, copy them back NOW - while the handle that holds them is still alive.  Called before the
+        engine is freed or rebuilt (reserve(), set_precision(), .to()), before any weight push and by state_dict()."""
+        if getattr(self, "_pending_pull", None) is None:
+            return
+        self._pending_pull = None
+        if self._handle is not None:
+            self._pull_from_handle(self._handle)
+
+    def _pull_from_handle(self, handle):
+        lib = _lib.load()
+        same_place = True
+        dev_index = self._handle_key[0] if self._handle_key else torch.cuda.current_device()
+        stream = C.c_void_p(torch.cuda.current_stream(dev_index).cuda_stream)   # ordered after the training kernels
+        with torch.no_grad():
+            for k, p in self.named_parameters():
+                if k == "learned_tgt":
+                    continue
+                # the library copies with cudaMemcpyDefault: the destination may be on any device or on the host
+                buf = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+                _lib.check(lib.sdvg_get_weight(handle, k.encode(), C.c_void_p(buf.data_ptr()), stream), handle)
+                p.copy_(buf)
+                same_place = same_place and p.is_cuda
+        if same_place and self._handle is handle:
+            self._weights_stamp = self._stamp()     # the engine already holds exactly these values
 
     def load_state_dict(self, *args, **kwargs):
         self._pending_pull = None            # loaded values supersede whatever an AdamTrainer left in the engine
@@ -78,6 +150,7 @@ class Transformer(nn.Module):
 
     def _free(self):
         if self._handle is not None:
+            self._sync_trained_weights()          # trained weights live only in the engine: rescue them first
             _lib.load().sdvg_destroy(self._handle)
             self._handle = None
 
@@ -109,6 +182,7 @@ class Transformer(nn.Module):
         lib = _lib.load()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         key = (dev_index, self.precision, tuple(sorted(self._limits.items())), self._arch())
+        self._sync_trained_weights()              # never push stale parameters over weights an optimizer step left behind
         if self._handle is None or self._handle_key != key:
             self._free()
             d, H, Le, Ld, E, ff = self._arch()
@@ -119,7 +193,7 @@ class Transformer(nn.Module):
             self._handle, self._handle_key, self._weights_stamp = h, key, None
         stamp = self._stamp()
         if stamp != self._weights_stamp:
-            for k, v in self.state_dict().items():
+            for k, v in super().state_dict().items():
                 if k == "learned_tgt":      # TransformerFuture's extra parameter is not used by forward
                     continue
                 t = v.detach()
@@ -143,8 +217,9 @@ class Transformer(nn.Module):
 
     def _check_eval(self):
         if self.training and self.dropout_p > 0:
-            raise RuntimeError("libsdvg implements the inference path (model.eval()); the training step with "
-                               "dropout is not part of this build")
+            raise RuntimeError("rollout()/predict() are the inference path: call model.eval() first (as prediction/predict.py:17 "
+                               "does).  Training goes through model(...) + loss.backward() in train() mode, or the fused "
+                               "sdvg_b200.AdamTrainer.step()")
 
     # ------------------------------------------------------------------ reference API
     def forward(self, src, tgt, tgt_mask=None, src_pad_mask=None, tgt_pad_mask=None, *, pe_index=None):
@@ -155,7 +230,8 @@ class Transformer(nn.Module):
         (extension; needed for B > 64, where the reference itself raises)."""
         if src_pad_mask is not None or tgt_pad_mask is not None:
             raise RuntimeError("padding masks are None at every reference call site and are not supported")
-        self._check_eval()
+        if self.training:
+            return self._forward_train(src, tgt, tgt_mask, pe_index)
         if src.dim() != 3 or tgt.dim() != 3 or src.size(0) != tgt.size(0) or src.size(2) != self.latent_dim \
                 or tgt.size(2) != self.latent_dim:
             raise RuntimeError(f"expected src (B,S,{self.latent_dim}) and tgt (B,S',{self.latent_dim}), got "
@@ -193,6 +269,38 @@ class Transformer(nn.Module):
                                             out.data_ptr(), C.c_void_p(stream)), h)
         return out
 
+    def _forward_train(self, src, tgt, tgt_mask, pe_index):
+        """model.train(): the call of trainers/trainer.py:141 - dropout active (the library's counter-based masks,
+        ``self.dropout_seed``), activations saved, and the result carries a grad_fn so that the reference's own
+        ``loss.backward()`` / ``optim.Adam(model.parameters()).step()`` work unchanged.  The fused fast path for the
+        same iteration is ``sdvg_b200.AdamTrainer.step``."""
+        if src.dim() != 3 or tgt.dim() != 3 or src.size(0) != tgt.size(0) or src.size(2) != self.latent_dim \
+                or tgt.size(2) != self.latent_dim:
+            raise RuntimeError(f"expected src (B,S,{self.latent_dim}) and tgt (B,S',{self.latent_dim}), got "
+                               f"{tuple(src.shape)} and {tuple(tgt.shape)}")
+        device = src.device
+        B, Ss, St = src.size(0), src.size(1), tgt.size(1)
+        if pe_index is None and B > 64:
+            raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b (64) at non-singleton "
+                               "dimension 0 (positional encoding is indexed by batch position; pass pe_index for B > 64)")
+        causal = isinstance(tgt_mask, str) and tgt_mask == "causal"
+        if not causal:
+            # every training call site of the reference passes get_tgt_mask(T) (trainers/trainer.py:137-141)
+            if tgt_mask is None or tuple(tgt_mask.shape) != (St, St) or not torch.equal(tgt_mask.detach().cpu().float(),
+                                                                                        self.get_tgt_mask(St)):
+                raise RuntimeError("the training forward pass implements the causal target mask of get_tgt_mask() "
+                                   "(the only mask the reference trains with)")
+        self.reserve(max_clips=B, max_tokens=max(Ss, St))
+        s = self._f32c(src.detach(), device)
+        t = self._f32c(tgt.detach(), device)
+        if pe_index is not None:
+            pe_index = pe_index.to(device=device, dtype=torch.int32).contiguous()
+            if pe_index.numel() != B:
+                raise RuntimeError("pe_index must have one entry per clip")
+        params = [p for k, p in self.named_parameters() if k != "learned_tgt"]
+        self.dropout_seed = int(getattr(self, "dropout_seed", 0))
+        return _TrainForward.apply(self, s, t, pe_index, *params)
+
     def get_tgt_mask(self, size) -> torch.Tensor:
         """models/transformer.py:70-89: (size,size) float CPU tensor, 0 on/below the diagonal, -inf above."""
         mask = torch.tril(torch.ones(size, size) == 1).float()
@@ -207,7 +315,12 @@ class Transformer(nn.Module):
     # ------------------------------------------------------------------ rollout (prediction/predict.py)
     def rollout(self, ctx, n_pred, window=5, *, faithful=False, residual=False, teacher=None, pe_index=None,
                 scale_in=1.0, scale_out=1.0, out=None):
-        """Batched autoregressive rollout on the device: ctx (B,C,E) -> (B,n_pred,E).  See sdvg_rollout."""
+        """Batched autoregressive rollout on the device: ctx (B,C,E) -> (B,n_pred,E).  See sdvg_rollout.
+
+        pe_index: the positional row of each clip (the reference indexes its table by BATCH position,
+        models/positional_encoding.py:35).  None = ``b mod 64``: the clips as one reference batch run in chunks of 64.
+        An int = that row for every clip: ``pe_index=0`` reproduces prediction/predict.py, whose DataLoader has
+        ``batch_size=1`` (:58), so every clip it rolls out is batch position 0.  Or an int32 tensor (B,)."""
         self._check_eval()
         if ctx.dim() != 3 or ctx.size(2) != self.latent_dim:
             raise RuntimeError(f"expected ctx (B,C,{self.latent_dim}), got {tuple(ctx.shape)}")
@@ -224,6 +337,10 @@ class Transformer(nn.Module):
                 raise RuntimeError("teacher must be (B, n_pred, E)")
             tptr = teacher.data_ptr()
         pe_ptr = None
+        if isinstance(pe_index, int):
+            if not 0 <= pe_index < 64:
+                raise RuntimeError("pe_index must be a row of the 64-row positional table")
+            pe_index = torch.full((B,), pe_index, dtype=torch.int32, device=device)
         if pe_index is not None:
             pe_index = pe_index.to(device=device, dtype=torch.int32).contiguous()
             if pe_index.numel() != B:
@@ -271,6 +388,9 @@ class TransformerFuture(Transformer):
                  dropout_p=0.1, *, frames_to_predict=None, **kw):
         super().__init__(num_tokens, dim_model, num_heads, num_encoder_layers, num_decoder_layers, dropout_p, **kw)
         if frames_to_predict is None:
+            if self.config is None:
+                raise ValueError("TransformerFuture(frame_size=...) needs frames_to_predict= (without frame_size it is read "
+                                 "from the yaml config like the reference, models/transformer_future.py:46)")
             frames_to_predict = self.config.FRAMES_TO_PREDICT[0]
         self.learned_tgt = nn.Parameter(torch.randn((1, frames_to_predict, self.latent_dim), dtype=torch.float32),
                                         requires_grad=True)

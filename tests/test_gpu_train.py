@@ -144,6 +144,33 @@ def test_c5_architecture_step_vs_oracle():
         assert ours <= TOLG + 2.0 * ref32, (k, ours, ref32)
 
 
+def test_c5_bench_shape_step_with_dropout_vs_same_mask_oracle():
+    """The bench shape of BASELINE config 5: 16 clips per GPU, DROPOUT_P 0.1 as in the yaml - one step against the
+    oracle run under the SAME dropout masks (oracle/dropout.py restates the library's counter-based hash).  Same
+    yardstick as above: float64 oracle, ours within 1e-4 plus twice the fp32 oracle's own distance from it."""
+    from oracle import dropout as D
+    c = sdvg_b200.CONFIGS["11_19_wallpushups_all_losses_test"]
+    arch = (c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"])
+    m, ref = build_pair(*arch, seed=0, frame_size=c["frame_size"])
+    m.dropout_p = 0.1
+    seed = 0x5EED_0C5
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-5, frames_to_predict=5, seed=seed, **CASES["c5"])
+    assert tr.dropout == 0.1
+    batch = OT.make_batch(16, 6, 1024, seed=12)
+    sd = ref.state_dict()
+    loss32, pred32, g32 = OT.train_grads_functional(sd, arch[1], batch, 5, drop=D.Dropper(0.1, seed, 1), **CASES["c5"])
+    loss64, pred64, g64 = OT.train_grads_functional({k: v.double() for k, v in sd.items()}, arch[1], batch.double(), 5,
+                                                    drop=D.Dropper(0.1, seed, 1), **CASES["c5"])
+    losses = tr.step(batch.to(DEV))
+    assert abs(float(losses[0]) - float(loss64)) <= 2e-5 * abs(float(loss64))
+    assert float((tr.prediction(16, 5).cpu().double() - pred64).abs().max() / pred64.abs().max()) < 1e-4
+    for k, gr in g64.items():
+        scale = float(gr.abs().max())
+        ours = float((tr.gradient(k).cpu().double() - gr).abs().max()) / scale
+        ref32 = float((g32[k].double() - gr).abs().max()) / scale
+        assert ours <= TOLG + 2.0 * ref32, (k, ours, ref32)
+
+
 def test_odd_widths_and_head_sizes():
     """d = 96 with 4 heads (head dim 24: not a multiple of 32, operand planes padded 96 -> 128 columns, 96-row weight
     tiles) and d = 32 with 4 heads (head dim 8), one encoder / zero... one decoder layer, 3-token windows."""
@@ -323,3 +350,106 @@ def test_dropout_training_matches_oracle_under_the_same_masks(p):
     # without dropout the same first batch gives a different loss (the masks really were applied)
     l0, _, _ = OT.train_grads_functional(ref.state_dict(), 2, OT.make_batch(4, 6, 256, seed=31), 5, **CASES["c5"])
     assert abs(float(l0) - losses_seen[0]) > 1e-3 * abs(float(l0))
+
+
+@pytest.mark.parametrize("tag", ["c5", "gdl1"])
+def test_reference_loop_body_runs_unmodified(tag):
+    """The literal body of Trainer.train_loop (trainers/trainer.py:126-165) with only the model import swapped:
+    ``pred = model(new_batch, y_input, tgt_mask)``, the reference's own torch criterion, ``opt.zero_grad();
+    loss.backward(); opt.step()`` with ``torch.optim.Adam(model.parameters())`` (:365) - against the golden values of the
+    unmodified reference (losses, gradient samples, weights after two steps)."""
+    from oracle import losses as OL
+    g = load_golden("train_step")
+    d, H, Le, Ld, E = (int(v) for v in g["arch"])
+    B, S, P = (int(v) for v in g["shape"])
+    model, ref = build_pair(d, H, Le, Ld, int(g["seed"]))
+    if sd_checksum(ref.state_dict()) != str(g["checksum"]):
+        pytest.skip("seeded init differs from the fixture's torch build")
+    lr = float(g["lr"])
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    loss_fn = OL.criterion(**CASES[tag])
+    model.train()
+    for step in range(2):
+        new_batch = OT.make_batch(B, S, E, seed=100 + step).to(DEV)
+        y_input = new_batch[:, :-1]
+        y_expected = new_batch[:, 1:]
+        y_expected = y_expected.permute(1, 0, 2)
+        tgt_mask = model.get_tgt_mask(y_input.size(1)).to(DEV)
+        pred = model(new_batch, y_input, tgt_mask)
+        loss = loss_fn(pred[-P:], y_expected[-P:])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        want = float(g[f"{tag}.loss{step}"])
+        assert abs(float(loss) - want) <= 2e-5 * abs(want), step
+        if step == 0:
+            assert float((pred.detach().cpu() - g[f"{tag}.pred0"]).abs().max() / g[f"{tag}.pred0"].abs().max()) < 1e-4
+            for k, p in model.named_parameters():
+                amax = float(g[f"{tag}.g.{k}.amax"])
+                assert float((sample(p.grad).cpu() - g[f"{tag}.g.{k}.s"]).abs().max()) <= TOLG * amax, k
+    for k, p in model.named_parameters():
+        err = (sample(p).cpu() - g[f"{tag}.w.{k}.s"]).abs()
+        assert float(err.max()) <= 2.1 * lr, k
+    # validation afterwards (model.eval(), no_grad) sees the weights torch's optimiser wrote
+    model.eval()
+    with torch.no_grad():
+        out = model(new_batch, y_input.contiguous(), "causal")
+    ref.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    ref.eval()
+    with torch.no_grad():
+        want = ref(new_batch.cpu(), y_input.cpu(), ref.get_tgt_mask(S - 1))
+    assert float((out.cpu() - want).abs().max() / want.abs().max()) < 1e-4
+
+
+def test_checkpoint_files_round_trip_with_the_reference_module(tmp_path):
+    """prediction/predict.py:51 and trainers/trainer.py:472-479: a state_dict FILE written by the reference module loads
+    into the drop-in, is trained one step, saved with torch.save(model.state_dict()) and loads back into the reference."""
+    torch.manual_seed(3)
+    ref = RefTransformer(0, 64, 2, 2, 2, 0.0, frame_size=64)
+    f_in, f_out = tmp_path / "ref_ckpt.pt", tmp_path / "ours_ckpt.pt"
+    torch.save(ref.state_dict(), f_in)
+    m = sdvg_b200.Transformer(0, 64, 2, 2, 2, 0.0, frame_size=64, precision="fp32")
+    m.load_state_dict(torch.load(f_in))
+    m = m.to(DEV)
+    batch = OT.make_batch(4, 6, 256, seed=21)
+    tr = sdvg_b200.AdamTrainer(m, lr=1e-3, frames_to_predict=5, **CASES["c5"])
+    tr.step(batch.to(DEV))
+    torch.save(m.state_dict(), f_out)
+    back = RefTransformer(0, 64, 2, 2, 2, 0.0, frame_size=64)
+    sd = torch.load(f_out, map_location="cpu")
+    assert sorted(sd) == sorted(ref.state_dict())
+    back.load_state_dict(sd)                                                   # strict: same keys, same shapes
+    moved = max(float((sd[k] - v).abs().max()) for k, v in ref.state_dict().items() if "pos_encoding" not in k)
+    assert moved > 1e-4                                                        # the file holds the TRAINED weights
+    back.eval()
+    m.eval()
+    x = batch[:, :5].contiguous()
+    with torch.no_grad():
+        want = back(x, x, back.get_tgt_mask(5))
+        got = m(x.to(DEV), x.to(DEV), "causal").cpu()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-4
+
+
+def test_trained_weights_survive_an_engine_rebuild():
+    """After AdamTrainer.step the trained weights live only in the engine.  Growing a workspace limit (a rollout with a
+    longer history), changing the precision or freeing the handle rebuilds the engine: the weights must be rescued
+    first, not replaced by the stale module parameters."""
+    twins = [build_pair(64, 2, 2, 2, seed=5)[0] for _ in range(2)]
+    batch = OT.make_batch(4, 6, 256, seed=7).to(DEV)
+    for m in twins:
+        sdvg_b200.AdamTrainer(m, lr=1e-3, frames_to_predict=5, **CASES["c5"]).step(batch)
+    want = {k: v.detach().clone() for k, v in twins[1].state_dict().items()}      # plain pull
+    m = twins[0]
+    before = {k: v.detach().clone() for k, v in torch.nn.Module.state_dict(m).items()}   # stale parameters, no pull
+    m.eval()
+    ctx = torch.randn(3, 40, 256, generator=torch.Generator().manual_seed(1)).to(DEV)
+    out = sdvg_b200.rollout(m, ctx, 2, 5)                   # history 42 > the default 32: reserve() -> engine rebuilt
+    got = m.state_dict()
+    assert any(not torch.equal(before[k], want[k]) for k in want)                # training did move the weights
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    twins[1].eval()
+    assert torch.equal(out, sdvg_b200.rollout(twins[1], ctx, 2, 5))             # and the rebuilt engine runs on them
+    m.set_precision("mixed")                                                      # another rebuild: still the trained weights
+    for k in want:
+        assert torch.equal(m.state_dict()[k], want[k]), k

@@ -65,8 +65,13 @@ def test_b65_raises_before_any_device_work():
     with pytest.raises(RuntimeError, match="padding masks"):
         m(x[:2], x[:2], None, torch.zeros(2, 2, dtype=torch.bool))
     m.train()
-    with pytest.raises(RuntimeError, match="inference path"):
+    # train() mode is the autograd bridge of trainers/trainer.py:141: causal mask only, CUDA only, rollouts need eval()
+    with pytest.raises(RuntimeError, match="causal target mask"):
         m(x[:2], x[:2])
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(x[:2], x[:2], m.get_tgt_mask(2))
+    with pytest.raises(RuntimeError, match="inference path"):
+        m.rollout(x[:2], 2)
 
 
 def test_configs_table():
@@ -216,3 +221,30 @@ def test_dropout_hash_restatement_matches_library_header(tmp_path):
                 key = D.site_key(seed, step, site)
                 want = [key] + [int(D.fmix32((idx * 0x9E3779B1 + key) & D.M32)) for idx in (0, 1, 12345, 4000000000)]
                 assert got == want, (seed, step, site)
+
+
+def test_latent_cache_reads_the_reference_npy_layout(tmp_path):
+    """utils/preprocess.py:27-33 stores one (1, 4, h, w) float32 array per frame next to the png; a clip is the sorted
+    file list and E = 4 h w in C order (utils/sd_utils.py:147-149)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(4)
+    clips = torch.randn(3, 7, 4, 8, 8, generator=g)
+    dirs = []
+    for b in range(3):
+        d = tmp_path / f"clip{b}"
+        d.mkdir()
+        for t in range(7):
+            np.save(d / f"frame_{t:03d}.npy", clips[b, t][None].numpy())          # what preprocess.py writes
+            (d / f"frame_{t:03d}.png").write_bytes(b"")                            # the images sit beside them
+        dirs.append(str(d))
+    x = sdvg_b200.load_latent_clips(dirs, frames=5)
+    assert tuple(x.shape) == (3, 5, 256) and x.dtype == torch.float32
+    assert torch.equal(x, clips[:, :5].reshape(3, 5, -1))
+    xs = sdvg_b200.load_latent_clips(dirs, frames=5, use_sos=True)
+    assert tuple(xs.shape) == (3, 6, 256) and bool((xs[:, 0] == sdvg_b200.SOS_VALUE).all()) and torch.equal(xs[:, 1:], x)
+    out_dir = tmp_path / "pred"
+    paths = sdvg_b200.save_latent_frames(str(out_dir), x[0])
+    assert np.load(paths[2]).shape == (1, 4, 8, 8)
+    assert torch.equal(sdvg_b200.load_latent_frames(paths), x[0])
+    with pytest.raises(ValueError):
+        sdvg_b200.load_latent_clips(dirs, frames=9)
