@@ -279,28 +279,33 @@ def run_extras(a, model_c2, world, rank, local, dev):
     if world > 1 and a.batch % world == 0:
         measure(model_c2, "c2_strong_scaling", "1_15_kitti_L1_64", a.batch // world, a.window, a.precision,
                 note=f"strong scaling of configs[1]: {a.batch} clips TOTAL over {world} GPUs, final all-gather inside the step")
-    # ---- C1: BASELINE configs[0], B = 8 (same architecture as C2), per-kernel launch chain
-    measure(model_c2, "c1_w5", "1_17_ball_complex_L1_64", 8, 5, a.precision, gather=False, note=hbm_note)
-    measure(model_c2, "c1_w10", "1_17_ball_complex_L1_64", 8, 10, a.precision, gather=False, note=hbm_note)
-    model_c2._free()
-    # ---- C1 through the persistent one-launch kernel (SDVG_PK=1, read when the engine is created)
+    # ---- C1: BASELINE configs[0], B = 8 (same architecture and weights as C2).  SDVG_PK (read when the engine is
+    # created) selects the per-kernel launch chain (0) or the persistent one-launch kernel (1); unset = automatic.
     prev = os.environ.get("SDVG_PK")
-    os.environ["SDVG_PK"] = "1"
+
+    def with_pk(flag):
+        model_c2._free()
+        os.environ["SDVG_PK"] = flag
     try:
+        with_pk("0")
+        measure(model_c2, "c1_w5", "1_17_ball_complex_L1_64", 8, 5, a.precision, gather=False, note=hbm_note + "; per-kernel launch chain")
+        measure(model_c2, "c1_w10", "1_17_ball_complex_L1_64", 8, 10, a.precision, gather=False, note=hbm_note + "; per-kernel launch chain")
+        measure(model_c2, "c1_w5_fp32", "1_17_ball_complex_L1_64", 8, 5, "fp32", gather=False, note="fp32-parity mode, per-kernel launch chain")
+        measure(model_c2, "c1_b1_fp32", "1_17_ball_complex_L1_64", 1, 5, "fp32", gather=False,
+                note="batch 1 - the reference's own inference regime (prediction/predict.py:58); per-kernel launch chain")
+        with_pk("1")
         measure(model_c2, "c1_w5_persistent", "1_17_ball_complex_L1_64", 8, 5, a.precision, gather=False,
                 note=hbm_note + "; the whole rollout is ONE launch of sdvg::persistent_kernel")
-        measure(model_c2, "c1_w5_persistent_fp32", "1_17_ball_complex_L1_64", 8, 5, "fp32", gather=False,
-                note="persistent kernel, fp32-parity mode (the case where it beats the launch chain)")
-        measure(model_c2, "c1_b1_persistent_fp32", "1_17_ball_complex_L1_64", 1, 5, "fp32", gather=False,
-                note="batch 1 - the reference's own inference regime (prediction/predict.py:58)")
+        measure(model_c2, "c1_w5_fp32_persistent", "1_17_ball_complex_L1_64", 8, 5, "fp32", gather=False,
+                note="fp32-parity mode, persistent kernel (the automatic choice for fp32 with <= 48 rows)")
+        measure(model_c2, "c1_b1_fp32_persistent", "1_17_ball_complex_L1_64", 1, 5, "fp32", gather=False,
+                note="batch 1, persistent kernel (the automatic choice)")
     finally:
         model_c2._free()
         if prev is None:
             os.environ.pop("SDVG_PK", None)
         else:
             os.environ["SDVG_PK"] = prev
-    measure(model_c2, "c1_b1_fp32", "1_17_ball_complex_L1_64", 1, 5, "fp32", gather=False, note="batch 1, per-kernel launch chain")
-    model_c2._free()
     torch.cuda.empty_cache()
     # ---- C3 / C4
     for name, cfg_name in (("c3", "11_27_ucf_final"), ("c4", "11_20_wallpushups_dim_2048")):

@@ -515,11 +515,12 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-struct AttnMmaSmem {                       // per warp
-  uint16_t q[8][kMmaRow];                  // query rows (reused for the output rows)
-  uint16_t k[8][kMmaRow];
-  uint16_t v[9][kMmaRow];                  // row 8 = zeros: every key row >= Sk points here
-};
+// Shared memory of one warp: [Sq query rows | Sk key rows | padding up to 8 rows] [Sk value rows] [one zero row].
+// Only the rows that exist are staged (the first version reserved 8 + 8 + 9 rows = 13.2 KB per warp, which capped the
+// SM at 16 resident warps of a kernel whose time is load latency; 5-token windows need 16 rows = 8.4 KB -> 26 warps).
+// ldmatrix rows beyond Sq / Sk alias row 0 of their operand (their scores are masked / their outputs never stored);
+// the first 8 rows double as the output staging area once the scores are done.
+__host__ __device__ inline int attn_mma_rows(int Sq, int Sk) { return (Sq + Sk > 8 ? Sq + Sk : 8) + Sk + 1; }
 
 template <bool BF16, int MASK>
 __global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constant__ AttnArgs a) {
@@ -531,27 +532,32 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constan
   const int warp_global = blockIdx.x * 4 + wib;
   if (warp_global >= a.clips * a.heads) return;
   const int b = warp_global / a.heads, h = warp_global - b * a.heads;
-  AttnMmaSmem& sm = reinterpret_cast<AttnMmaSmem*>(attn_smem)[wib];
   const int Sq = a.Sq, Sk = a.Sk;
+  const int qk_rows = Sq + Sk > 8 ? Sq + Sk : 8;
+  uint16_t* smw = reinterpret_cast<uint16_t*>(attn_smem) + static_cast<size_t>(wib) * attn_mma_rows(Sq, Sk) * kMmaRow;
+  uint16_t* sq = smw;                                   // [Sq] query rows (rows 0..7 of this block: output staging later)
+  uint16_t* sk = smw + Sq * kMmaRow;                    // [Sk] key rows
+  uint16_t* sv = smw + qk_rows * kMmaRow;               // [Sk] value rows + the zero row (every key >= Sk points there)
   const uint16_t* qb = reinterpret_cast<const uint16_t*>(a.q) + static_cast<size_t>(b) * a.q_clip_stride + h * kMmaHd;
   const uint16_t* kb = reinterpret_cast<const uint16_t*>(a.k) + static_cast<size_t>(b) * a.kv_clip_stride + h * kMmaHd;
   const uint16_t* vb = reinterpret_cast<const uint16_t*>(a.v) + static_cast<size_t>(b) * a.kv_clip_stride + h * kMmaHd;
 
   // ---- stage Q, K, V rows (512 B each: 32 lanes x 16 B) and the zero row
-  for (int r = a.q_first; r < Sq; ++r) cp_async16(ptx::smem_u32(&sm.q[r][lane * 8]), qb + static_cast<size_t>(r) * a.ldq + lane * 8);
+  for (int r = a.q_first; r < Sq; ++r) cp_async16(ptx::smem_u32(sq + r * kMmaRow + lane * 8), qb + static_cast<size_t>(r) * a.ldq + lane * 8);
   for (int r = 0; r < Sk; ++r) {
-    cp_async16(ptx::smem_u32(&sm.k[r][lane * 8]), kb + static_cast<size_t>(r) * a.ldkv + lane * 8);
-    cp_async16(ptx::smem_u32(&sm.v[r][lane * 8]), vb + static_cast<size_t>(r) * a.ldkv + lane * 8);
+    cp_async16(ptx::smem_u32(sk + r * kMmaRow + lane * 8), kb + static_cast<size_t>(r) * a.ldkv + lane * 8);
+    cp_async16(ptx::smem_u32(sv + r * kMmaRow + lane * 8), vb + static_cast<size_t>(r) * a.ldkv + lane * 8);
   }
-  *reinterpret_cast<uint4*>(&sm.v[8][lane * 8]) = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(sv + Sk * kMmaRow + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
 
-  // ---- S = Q K^T  (16 x 8 tile, rows 8..15 alias rows 0..7 and are ignored)
+  // ---- S = Q K^T  (16 x 8 tile; query rows outside [q_first, Sq) and key rows >= Sk alias a staged row: masked below)
   const int mid = lane >> 3, mr = lane & 7;           // ldmatrix: matrix id, row inside the matrix
-  const uint32_t q_addr = ptx::smem_u32(&sm.q[mr][(mid >> 1) * 8]);      // A: M0 rows0-7 k0-7 | M1 rows8-15(alias) k0-7 | M2 k8-15 | M3
-  const uint32_t k_addr = ptx::smem_u32(&sm.k[mr][(mid & 1) * 8]);       // B (x2, lanes 0-15): n rows, k 0-7 | k 8-15
+  const int qrow = (mr >= a.q_first && mr < Sq) ? mr : a.q_first, krow = mr < Sk ? mr : 0;
+  const uint32_t q_addr = ptx::smem_u32(sq + qrow * kMmaRow + (mid >> 1) * 8);   // A: M0 rows0-7 k0-7 | M1 rows8-15(alias) k0-7 | M2 k8-15 | M3
+  const uint32_t k_addr = ptx::smem_u32(sk + krow * kMmaRow + (mid & 1) * 8);    // B (x2, lanes 0-15): n rows, k 0-7 | k 8-15
   float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int kk = 0; kk < kMmaHd / 16; ++kk) {
@@ -588,10 +594,10 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constan
 
   // ---- O^T = V^T P^T : 16 tiles of 16 head elements x 8 queries
   // A through ldmatrix.trans of V ([key][hd]): M0 keys0-7 hd m0..+7 | M1 keys0-7 hd m0+8.. | M2 keys8-15 | M3 keys8-15
-  const int vrow = (mid >> 1) ? 8 : (mr < Sk ? mr : 8);               // keys >= Sk (and all of 8..15) -> zero row
-  const uint32_t v_addr = ptx::smem_u32(&sm.v[vrow][(mid & 1) * 8]);
-  __syncwarp();                                                       // everyone is done reading sm.q
-  uint16_t* so = &sm.q[0][0];
+  const int vrow = (mid >> 1) ? Sk : (mr < Sk ? mr : Sk);             // keys >= Sk (and all of 8..15) -> zero row
+  const uint32_t v_addr = ptx::smem_u32(sv + vrow * kMmaRow + (mid & 1) * 8);
+  __syncwarp();                                                       // everyone is done reading the query / key rows
+  uint16_t* so = smw;                                                 // 8 staging rows over the query + key rows
 #pragma unroll
   for (int m = 0; m < kMmaHd / 16; ++m) {
     uint32_t af[4];
@@ -774,11 +780,13 @@ inline cudaError_t launch_attention_mma16(const AttnArgs& a, cudaStream_t stream
 inline cudaError_t launch_attention_mma(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq > 8 || a.Sk > 8) return launch_attention_mma16(a, stream);
   const int grid = ceil_div(a.clips * a.heads, 4);
-  const size_t smem = 4 * sizeof(AttnMmaSmem);
+  const size_t smem = 4 * static_cast<size_t>(attn_mma_rows(a.Sq, a.Sk)) * kMmaRow * sizeof(uint16_t);
+  const size_t smem_max = 4 * static_cast<size_t>(attn_mma_rows(8, 8)) * kMmaRow * sizeof(uint16_t);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
+    const size_t smem = smem_max;
     cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

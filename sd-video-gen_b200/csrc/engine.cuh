@@ -132,9 +132,12 @@ class Engine {
   // ---- persistent small-batch path (persistent.cuh): while pk_rec is set, gemm() / layernorm() / attention() /
   // pack() / add_rows() append ops to pk_ops instead of launching, so run_model() and rollout_enqueue() are the one
   // description of the model for both the per-kernel path and the one-launch path
-  bool use_pk = false;         // SDVG_PK=1 enables: measured on B200 (profiles/README.md, round 2) a pass costs ~8 us per
-                               // dependent GEMM stage inside the kernel vs ~7 us per kernel boundary of the launch chain, so the
-                               // one-launch path only wins in fp32 (split) mode at window 5; it stays selectable and tested
+  // SDVG_PK=1: whenever the rows fit; SDVG_PK=0: never; unset: automatic - where it measured faster than the launch
+  // chain on B200 (profiles/README.md, round 2): fp32 (split) mode with at most 48 rows, i.e. the reference's own
+  // batch-1 inference (-13 %) up to 8 clips x window 5 (-3 %).  In the 16-bit modes a dependent GEMM stage inside the
+  // kernel (~8 us) costs more than a kernel boundary of the PDL + graph launch chain (~7 us).
+  int pk_mode = -1;            // -1 automatic, 0 off, 1 on
+  bool use_pk = true;
   bool pk_rec = false;
   bool pk_bad = false;         // an op the persistent kernel cannot run was recorded: fall back to per-kernel launches
   std::vector<PkOp> pk_ops;
@@ -451,7 +454,7 @@ class Engine {
         return fail_cuda(e, "cache alloc");
     }
     if (const char* v = std::getenv("SDVG_LAZY_LN")) lazy_ln = std::atoi(v) != 0;
-    if (const char* v = std::getenv("SDVG_PK")) use_pk = std::atoi(v) != 0;
+    if (const char* v = std::getenv("SDVG_PK")) { pk_mode = std::atoi(v) != 0 ? 1 : 0; use_pk = pk_mode == 1; }
     if (const char* v = std::getenv("SDVG_KSPLIT")) use_ksplit = std::atoi(v) != 0;
     if (tc() && ((e = dalloc(&ks_ws, static_cast<size_t>(num_sms) * kTcBM * 128)) != cudaSuccess ||
                  (e = dalloc(&ks_flags, 1024)) != cudaSuccess))
@@ -967,7 +970,11 @@ class Engine {
   bool pk_coop = true;
 
   // rows the widest GEMM of a pass sees
-  bool pk_eligible(int rows) { return tc() && rows <= kPkMaxRows && pk_init(); }
+  bool pk_eligible(int rows) {
+    if (!tc() || rows > kPkMaxRows || !use_pk) return false;
+    if (pk_mode < 0 && !(split_all() && rows <= 48)) return false;      // automatic: only where it measured faster
+    return pk_init();
+  }
 
   // Latents (B, S, E) fp32 (contiguous or gathered from history slots) -> operand buffer `dst`.
   cudaError_t ingest(const float* src, long long clip_stride, long long slot_stride, const int* slot_list, int B,

@@ -294,6 +294,7 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
       Linear L;
       L.N = N; L.K = K; L.bias = bias; L.split = split;
       L.p.hi = w_hi; L.p.lo = w_lo; L.p.rows = N; L.p.cols = K; L.p.ld = Kp;
+      tmp_eng.use_pk = true; tmp_eng.pk_mode = 1;   // this entry point asks for the persistent kernel explicitly
       if (err != cudaSuccess || !tmp_eng.pk_eligible(M)) { cleanup(); g_create_error = "sdvg_gemm: persistent kernel unavailable (M > 128 or no cluster launch)"; return SDVG_ERR_UNSUPPORTED; }
       tmp_eng.pk_begin();
       int repeat = 1;   // SDVG_PK_REPEAT=n: the same op n times in one program (per-op cost in steady state)

@@ -182,9 +182,8 @@ class Transformer(nn.Module):
         lib = _lib.load()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         key = (dev_index, self.precision, tuple(sorted(self._limits.items())), self._arch())
-        self._sync_trained_weights()              # never push stale parameters over weights an optimizer step left behind
         if self._handle is None or self._handle_key != key:
-            self._free()
+            self._free()                          # (rescues trained weights out of the old engine first)
             d, H, Le, Ld, E, ff = self._arch()
             cfg = _lib.SdvgConfig(d, H, Le, Ld, E, ff, 1e-5, self._limits["max_clips"], self._limits["max_tokens"],
                                   self._limits["max_history"], _lib.PRECISIONS[self.precision], dev_index)
@@ -192,6 +191,11 @@ class Transformer(nn.Module):
             _lib.check(lib.sdvg_create(C.byref(cfg), C.byref(h)))
             self._handle, self._handle_key, self._weights_stamp = h, key, None
         stamp = self._stamp()
+        if stamp != self._weights_stamp and getattr(self, "_pending_pull", None) is not None:
+            # the parameters moved (.to(), in-place edit) while newer weights still sit in the engine: never push stale
+            # values over what an optimizer step left there - bring the trained weights home first
+            self._sync_trained_weights()
+            stamp = self._stamp()
         if stamp != self._weights_stamp:
             for k, v in super().state_dict().items():
                 if k == "learned_tgt":      # TransformerFuture's extra parameter is not used by forward

@@ -1,4 +1,12 @@
-timeout 120 python tools/pk_check.py gemm 2>&1 | grep -v -i warn | grep -E "fp16|fp32|worst|Error|error" 
-timeout 200 python tools/pk_check.py forward 2>&1 | grep -v -i warn | grep -E "forward d256|Error|error" 
-timeout 300 python tools/pk_check.py rollout 2>&1 | grep -v -i warn | grep -E "rollout|max-rel|Error|error"
-SDVG_PK_TRACE=8,0,533 timeout 100 python tools/pk_trace_rollout.py mixed 5 2>&1 | grep -v -i warn | grep -v TransformerEnc
+set -x
+timeout 300 python -m pytest tests/test_gpu_train.py -q -m gpu -k "c5_bench_shape" 2>&1 | grep -E "^E|passed|failed" | head -20 > gpurun_out/t1.log
+timeout 300 python bench_train.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/train_r2a.json 2>/dev/null
+timeout 300 python bench_train.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/train_r2b.json 2>/dev/null
+timeout 300 python __graft_entry__.py smoke 2>&1 | grep -v -i warn | tail -6 > gpurun_out/smoke.log
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 > gpurun_out/gputest.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel --launch-skip 700 -c 6 -o gpurun_out/r2_gemm_full python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
+ncu -i gpurun_out/r2_gemm_full.ncu-rep --page raw --csv > gpurun_out/r2_gemm_ncu_full_raw.csv 2>/dev/null
+SDVG_PK=1 PK_REPEAT=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:persistent_kernel --launch-skip 2 -c 1 -o gpurun_out/r2_pk_full python tools/pk_trace_rollout.py mixed 5 > gpurun_out/ncu_pk.log 2>&1
+ncu -i gpurun_out/r2_pk_full.ncu-rep --page raw --csv > gpurun_out/r2_pk_ncu_full_raw.csv 2>/dev/null
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 2400 --csv --log-file gpurun_out/r2_launches_bench_mixed.csv python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+ls -la gpurun_out/*.ncu-rep

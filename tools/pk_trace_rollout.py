@@ -13,4 +13,6 @@ m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encode
                           frame_size=64, precision=prec, max_clips=B, max_tokens=10, max_history=C + P).eval().cuda()
 ctx = torch.randn(B, C, 256, generator=torch.Generator().manual_seed(1234)).cuda()
 out = m.rollout(ctx, P, W)
+for _ in range(int(os.environ.get('PK_REPEAT', '0'))):
+    m.rollout(ctx, P, W, out=out)
 torch.cuda.synchronize()
