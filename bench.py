@@ -15,8 +15,9 @@ value   : whole-job latent frames/s with the context already resident in HBM.
 e2e     : same through host buffers (pinned H2D of the context and D2H of the predictions inside the timed region).
 roofline: tensor-core GEMM kernel class (the dominant kernel): algorithmic 2MNK FLOPs / CUDA-event time of those
           launches, measured live in an instrumented pass of the same workload, against MEASURED_PEAKS.json.
-cpu_baseline / --impl reference: the oracle port of the reference path (oracle/ref_module.py on torch CPU, i.e.
-          the reference's own nn.Transformer arithmetic) on the host cores, on a bounded sample.
+cpu_baseline / --impl reference: the UNMODIFIED reference module (baseline/_ref, installed by oracle/install_ref.py in the
+          build container; kind "reference") - or, when that is absent, the oracle's restatement of it
+          (oracle/ref_module.py; kind "port") - on torch CPU with all host cores, on a bounded sample.
 """
 import argparse
 import json
@@ -109,13 +110,20 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_setup(cfg, seed=0):
+def cpu_reference_setup(cfg, config_name=None, seed=0):
+    """(model, kind, what): the UNMODIFIED reference module from baseline/_ref (oracle/install_ref.py; kind "reference")
+    when it was installed in the build container, else the oracle's restatement of it (kind "port").  Both are
+    torch.nn.Transformer underneath with bit-identical seeded weights (tests/test_oracle_golden.py)."""
     import torch
+    from oracle import install_ref
+    arch = (cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"], cfg["dropout_p"])
+    m = install_ref.load_reference(config_name, arch, seed) if config_name else None
+    if m is not None and m.height == cfg["frame_size"]:
+        return m, "reference", "baseline/_ref/models/transformer.py (the unmodified reference module, fp32, torch CPU)"
     from oracle.ref_module import RefTransformer
     torch.manual_seed(seed)
-    m = RefTransformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"],
-                       cfg["dropout_p"], frame_size=cfg["frame_size"]).eval()
-    return m
+    m = RefTransformer(0, *arch, frame_size=cfg["frame_size"]).eval()
+    return m, "port", "oracle/ref_module.py (torch.nn.Transformer, fp32)"
 
 
 def cpu_reference_step(model, ctx, n_pred, window):
@@ -136,7 +144,7 @@ def run_reference_arm(a, cfg, E):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = cpu_reference_setup(cfg)
+    model, kind, what = cpu_reference_setup(cfg, a.config)
     clips, n_pred = 64, a.cpu_sample_steps
     ctx = torch.randn(clips, a.context, E, generator=torch.Generator().manual_seed(1234))
     for _ in range(max(1, min(a.warmup, 2))):
@@ -148,14 +156,15 @@ def run_reference_arm(a, cfg, E):
     T = sum(times) / len(times)
     value = clips * n_pred / T
     sample = (f"per step: one 64-clip chunk (the reference's batch limit) x {n_pred} rollout steps of the same "
-              f"model/window; {a.steps} steps timed; threads={torch.get_num_threads()}")
+              f"model/window; {a.steps} steps timed; threads={torch.get_num_threads()}; {what}, rollout loop of "
+              f"prediction/predict.py:143-197 as restated in oracle/rollout.py")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{a.config} rollout, {a.context} ctx -> {a.pred} pred, window {a.window}",
                    "arch": cfg, "sample_clips": clips, "sample_pred": n_pred},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -463,14 +472,14 @@ def run_ours(a, cfg, E):
             import torch as _t
             cores = os.cpu_count() or 1
             _t.set_num_threads(cores)
-            cpu_model = cpu_reference_setup(cfg)
+            cpu_model, kind, what = cpu_reference_setup(cfg, a.config)
             cctx = ctx_host[:64]
             cpu_reference_step(cpu_model, cctx[:8], 1, W)
             out_cpu, dt = cpu_reference_step(cpu_model, cctx, a.cpu_sample_steps, W)
             line["cpu_baseline"] = {
-                "value": 64 * a.cpu_sample_steps / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                "value": 64 * a.cpu_sample_steps / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": kind,
                 "sample": f"first 64 clips (the reference's batch limit) x {a.cpu_sample_steps} rollout steps of the same "
-                          f"workload, {dt:.1f} s of CPU time; oracle/ref_module.py (torch.nn.Transformer, fp32)"}
+                          f"workload, {dt:.1f} s of CPU time; {what}"}
             # free parity read-out on the sample (teacher-free first frames)
             from oracle import rollout as R
             err = R.max_rel_per_frame(out[:64, :a.cpu_sample_steps].cpu(), out_cpu)
