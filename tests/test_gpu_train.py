@@ -159,9 +159,10 @@ def test_c5_bench_shape_step_with_dropout_vs_same_mask_oracle():
         other row <= 1.3e-5) and every tensor upstream of it by a dense ~3e-4 (one token of 80 carries a 2 % different
         gradient).
     torch's own fp32 run is 3e-4 ... 3e-2 from its float64 run on these tensors for the same reason, on different rows.
-    So the gradient bounds here are the kink-tolerant ones - per tensor max-rel <= 1e-1 (one flipped row) and relative Frobenius error
-    <= 1e-2, median tensor max-rel <= 5e-3 - which still catch any systematic error (a wrong mask, tile or scale is O(1)
-    on whole tensors); elementwise 1e-4 agreement is tested where no kink is hit (the other tests of this file)."""
+    So the gradient bounds here are the kink-tolerant ones - per tensor max-rel <= 1e-1 (one flipped row) and relative
+    Frobenius error <= 5e-2, median tensor max-rel <= 5e-3, relative error of the WHOLE gradient vector <= 5e-3 - which
+    still catch any systematic error (a wrong mask, tile or scale is O(1) on whole tensors); elementwise 1e-4 agreement
+    is tested where no kink is hit (the other tests of this file)."""
     from oracle import dropout as D
     c = sdvg_b200.CONFIGS["11_19_wallpushups_all_losses_test"]
     arch = (c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"])
@@ -177,13 +178,17 @@ def test_c5_bench_shape_step_with_dropout_vs_same_mask_oracle():
         losses = tr.step(batch.to(DEV))
         assert abs(float(losses[0]) - float(loss64)) <= 2e-5 * abs(float(loss64)), bseed
         assert float((tr.prediction(16, 5).cpu().double() - pred64).abs().max() / pred64.abs().max()) < 1e-4, bseed
-        worst, fro_worst, per_tensor = 0.0, 0.0, []
+        worst, fro_worst, per_tensor, num, den = 0.0, 0.0, [], 0.0, 0.0
         for k, gr in g64.items():
             d = tr.gradient(k).cpu().double() - gr
             per_tensor.append(float(d.abs().max() / gr.abs().max()))
             worst = max(worst, per_tensor[-1])
             fro_worst = max(fro_worst, float(d.norm() / gr.norm()))
-        assert worst <= 1e-1 and fro_worst <= 1e-2, (bseed, worst, fro_worst)
+            num += float(d.pow(2).sum()); den += float(gr.pow(2).sum())
+        # one flipped unit is one row of a weight gradient (<= 1e-1 of the tensor's maximum) or ONE element of a 2048-element
+        # bias gradient (a few per cent of its norm); over the whole gradient vector the kinks are a small perturbation
+        assert worst <= 1e-1 and fro_worst <= 5e-2, (bseed, worst, fro_worst)
+        assert (num / den) ** 0.5 <= 5e-3, (bseed, (num / den) ** 0.5)
         assert sorted(per_tensor)[len(per_tensor) // 2] <= 5e-3, bseed
 
 
