@@ -40,11 +40,13 @@ def make_batch(B, S, E, seed, sos=True):
     return x
 
 
-def train_grads_functional(state_dict, n_heads, new_batch, frames_to_predict, pe_index=None, drop=None, **loss_kw):
+def train_grads_functional(state_dict, n_heads, new_batch, frames_to_predict, pe_index=None, drop=None, return_dpred=False,
+                           **loss_kw):
     """Same iteration on the op-by-op restatement (oracle/functional.py) under autograd - used where hooks are needed:
     ``pe_index`` (data-parallel shards) and ``drop`` (an oracle.dropout.Dropper: training-mode dropout with the
     library's own masks, DROPOUT_P of the reference's configs).  Returns (loss, pred, {name: grad}) for the float
-    parameters of ``state_dict`` (the positional table is a buffer and gets no gradient)."""
+    parameters of ``state_dict`` (the positional table is a buffer and gets no gradient); with ``return_dpred`` also
+    dL/dpred (S_tgt, B, E) - the upstream gradient ``loss.backward()`` hands to the model's backward pass."""
     from . import functional as F
     sd = {k: v.detach().clone() for k, v in state_dict.items()}
     names = [k for k in sd if k != "positional_encoder.pos_encoding"]
@@ -53,6 +55,11 @@ def train_grads_functional(state_dict, n_heads, new_batch, frames_to_predict, pe
     y_input = new_batch[:, :-1]
     y_expected = new_batch[:, 1:].permute(1, 0, 2)
     pred = F.forward(sd, new_batch, y_input, n_heads, F.causal_mask(y_input.size(1), new_batch.dtype), pe_index=pe_index, drop=drop)
+    if return_dpred:
+        pred.retain_grad()
     loss = losses.criterion(**loss_kw)(pred[-frames_to_predict:], y_expected[-frames_to_predict:])
     loss.backward()
-    return loss.detach(), pred.detach(), {k: sd[k].grad.detach().clone() for k in names}
+    grads = {k: sd[k].grad.detach().clone() for k in names}
+    if return_dpred:
+        return loss.detach(), pred.detach(), grads, pred.grad.detach().clone()
+    return loss.detach(), pred.detach(), grads

