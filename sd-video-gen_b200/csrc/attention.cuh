@@ -490,6 +490,10 @@ __global__ void __launch_bounds__(128) attention_exact16_kernel(const __grid_con
 inline bool& attention_mma_enabled() { static bool on = true; return on; }  // SDVG_ATTN_MMA=0 disables
 constexpr int kMmaHd = 256;
 constexpr int kMmaRow = kMmaHd + 8;   // halves per smem row
+#ifndef SDVG_ATTN_GROUP
+#define SDVG_ATTN_GROUP 4
+#endif
+constexpr int kAttnMmaGroup = SDVG_ATTN_GROUP;   // K steps / output tiles whose fragments are in flight together
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -558,14 +562,27 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constan
   const int qrow = (mr >= a.q_first && mr < Sq) ? mr : a.q_first, krow = mr < Sk ? mr : 0;
   const uint32_t q_addr = ptx::smem_u32(sq + qrow * kMmaRow + (mid >> 1) * 8);   // A: M0 rows0-7 k0-7 | M1 rows8-15(alias) k0-7 | M2 k8-15 | M3
   const uint32_t k_addr = ptx::smem_u32(sk + krow * kMmaRow + (mid & 1) * 8);    // B (x2, lanes 0-15): n rows, k 0-7 | k 8-15
-  float sc[4] = {0.f, 0.f, 0.f, 0.f};
+  // (fragments of four K steps are loaded ahead of the four HMMAs that use them, and the steps alternate between two
+  // accumulators: ncu showed every HMMA of the plain loop stalled on its own ldmatrix (short scoreboard 30 %) and on
+  // the previous HMMA's accumulator)
+  float sc[4] = {0.f, 0.f, 0.f, 0.f}, sc2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int kk = 0; kk < kMmaHd / 16; ++kk) {
-    uint32_t af[4], bf[2];
-    ldmatrix_x4(af, q_addr + kk * 32);
-    ldmatrix_x2(bf, k_addr + kk * 32);
-    mma_16816<BF16>(sc, af, bf);
+  constexpr int G = kAttnMmaGroup;
+  for (int kk = 0; kk < kMmaHd / 16; kk += G) {
+    uint32_t af[G][4], bf[G][2];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      ldmatrix_x4(af[u], q_addr + (kk + u) * 32);
+      ldmatrix_x2(bf[u], k_addr + (kk + u) * 32);
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      if (u & 1) mma_16816<BF16>(sc2, af[u], bf[u]);
+      else mma_16816<BF16>(sc, af[u], bf[u]);
+    }
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) sc[e] += sc2[e];
   // ---- softmax over the keys of row g = lane / 4 (this thread holds keys 2t, 2t+1)
   const int g = lane >> 2, t = lane & 3;
   const float scale2 = a.scale * kLog2e;
@@ -599,23 +616,32 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __grid_constan
   __syncwarp();                                                       // everyone is done reading the query / key rows
   uint16_t* so = smw;                                                 // 8 staging rows over the query + key rows
 #pragma unroll
-  for (int m = 0; m < kMmaHd / 16; ++m) {
-    uint32_t af[4];
-    ldmatrix_x4_trans(af, v_addr + m * 32);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_16816<BF16>(o, af, pb);
-    // o[0], o[1] = O[q = 2t, 2t+1][hd = 16 m + g];  o[2], o[3] = same queries, hd = 16 m + g + 8
-    const int hd0 = m * 16 + g;
-    if constexpr (BF16) {
-      so[(2 * t) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[0]));
-      so[(2 * t + 1) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[1]));
-      so[(2 * t) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[2]));
-      so[(2 * t + 1) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[3]));
-    } else {
-      so[(2 * t) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[0]));
-      so[(2 * t + 1) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[1]));
-      so[(2 * t) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[2]));
-      so[(2 * t + 1) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[3]));
+  for (int m0 = 0; m0 < kMmaHd / 16; m0 += G) {
+    // G independent tiles at a time: their ldmatrix and HMMA latencies overlap, the conversions follow
+    uint32_t af[G][4];
+    float o[G][4];
+#pragma unroll
+    for (int u = 0; u < G; ++u) ldmatrix_x4_trans(af[u], v_addr + (m0 + u) * 32);
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      o[u][0] = 0.f; o[u][1] = 0.f; o[u][2] = 0.f; o[u][3] = 0.f;
+      mma_16816<BF16>(o[u], af[u], pb);
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      // o[0], o[1] = O[q = 2t, 2t+1][hd = 16 m + g];  o[2], o[3] = same queries, hd = 16 m + g + 8
+      const int hd0 = (m0 + u) * 16 + g;
+      if constexpr (BF16) {
+        so[(2 * t) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[u][0]));
+        so[(2 * t + 1) * kMmaRow + hd0] = __bfloat16_as_ushort(__float2bfloat16_rn(o[u][1]));
+        so[(2 * t) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[u][2]));
+        so[(2 * t + 1) * kMmaRow + hd0 + 8] = __bfloat16_as_ushort(__float2bfloat16_rn(o[u][3]));
+      } else {
+        so[(2 * t) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[u][0]));
+        so[(2 * t + 1) * kMmaRow + hd0] = __half_as_ushort(__float2half_rn(o[u][1]));
+        so[(2 * t) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[u][2]));
+        so[(2 * t + 1) * kMmaRow + hd0 + 8] = __half_as_ushort(__float2half_rn(o[u][3]));
+      }
     }
   }
   __syncwarp();
