@@ -48,6 +48,16 @@ struct Epilogue {
   const float2* ln_stats = nullptr;
   const float* ln_w = nullptr;
   const float* ln_b = nullptr;
+  // LayerNorm folded into the neighbouring GEMMs (large batches, 16-bit modes; Engine::fold_*):
+  //  * consumer (ln_in != 0): the A planes hold the PRE-norm sums y and the weight planes are W diag(gamma), so
+  //      acc = sum_k y_k gamma_k W_nk  and  LayerNorm(y) W^T + b = rstd[row] * (acc - mean[row] * c[col]) + b'[col]
+  //    with ln_stats = (mean, rstd) per row, ln_w = c (row sums of the folded planes), bias = b' = b + W beta;
+  //  * producer (stat_out != nullptr): besides its outputs, every epilogue warp leaves the (sum, sum of squares) of
+  //    the values it stored, per row and column slot: stat_out[row * stat_ld + slot] - summed in fixed slot order by
+  //    ln_stats_finalize_kernel (deterministic), so no kernel ever reads the row again to normalise it.
+  int ln_in = 0;
+  float2* stat_out = nullptr;
+  int stat_ld = 0;
   // training (backward GEMMs): alpha_dev multiplies like alpha but is read from device memory (1 / loss scale);
   // gate zeroes the value where gate[row][col] <= 0 (ReLU backward against the saved activation), before the residual
   const float* alpha_dev = nullptr;
@@ -96,6 +106,10 @@ __device__ __forceinline__ int epi_pe_row(const Epilogue& e, int row) {
 
 __device__ __forceinline__ float epi_value(const Epilogue& e, float acc, int row, int col, int pe_row) {
   float v = acc;
+  if (e.ln_in) {
+    const float2 st = __ldg(e.ln_stats + row);
+    v = st.y * (v - st.x * __ldg(e.ln_w + col));
+  }
   if (e.bias) v += __ldg(e.bias + col);
   v *= e.alpha;
   if (e.alpha_dev) v *= __ldg(e.alpha_dev);

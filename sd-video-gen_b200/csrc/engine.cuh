@@ -52,15 +52,23 @@ struct ActBuf {
   Planes p;
 };
 
+struct LNParam { const float* w = nullptr; const float* b = nullptr; };
+
 struct Linear {
   int N = 0, K = 0;
   const float* w32 = nullptr;
   const float* bias = nullptr;
   Planes p;
   bool split = false;
+  // LayerNorm folded into this GEMM (Epilogue::ln_in): planes of W diag(gamma), c = their row sums, b' = b + W beta,
+  // for the one LayerNorm whose output this projection always consumes (fold_norm); built by Engine::refold()
+  bool has_fold = false;
+  Planes pf;
+  float* fold_c = nullptr;
+  float* fold_b = nullptr;
+  LNParam fold_norm;
 };
 
-struct LNParam { const float* w = nullptr; const float* b = nullptr; };
 struct AttnWeights { Linear qkv, q, kv, out; };
 struct EncLayer { AttnWeights sa; Linear ff1, ff2; LNParam n1, n2; };
 struct DecLayer { AttnWeights sa, ca; Linear ff1, ff2; LNParam n1, n2, n3; };
@@ -127,6 +135,13 @@ class Engine {
   bool use_prune = true;     // last-decoder-layer pruning in rollouts (SDVG_PRUNE=0 disables)
   bool lazy_ln = true;       // deferred LayerNorm of the residual stream (SDVG_LAZY_LN=0 disables), see ResSrc
   float2* ln_stats = nullptr;  // [max_rows] (mean, rstd) left behind by the last LayerNorm kernel
+  // LayerNorm folded into the neighbouring GEMMs at large batch (SDVG_LN_FOLD, 16-bit non-split modes): the producer's
+  // epilogue leaves per-row partial sums in ln_part, the consumer reads the pre-norm planes through gamma-scaled weights
+  bool use_fold = true;        // SDVG_LN_FOLD=0 disables (same-box A/B on B200: 50.0 -> 48.2 ms per C2 step, profiles/README.md round 2)
+  int fold_min_rows = 512;
+  float2* ln_part = nullptr;   // [max_rows][fold_ld]
+  int fold_ld = 0;
+  int last_stat_slots = 0;     // column slots the last stat_out GEMM wrote per row (depends on its tile plan)
   int* pe_mod64 = nullptr;   // [max_clips] b mod 64
 
   // ---- persistent small-batch path (persistent.cuh): while pk_rec is set, gemm() / layernorm() / attention() /
@@ -460,6 +475,33 @@ class Engine {
                  (e = dalloc(&ks_flags, 1024)) != cudaSuccess))
       return fail_cuda(e, "split-K workspace alloc");
     if ((e = dalloc(&ln_stats, static_cast<size_t>(max_rows))) != cudaSuccess) return fail_cuda(e, "stats alloc");
+    if (const char* v = std::getenv("SDVG_LN_FOLD")) use_fold = std::atoi(v) != 0;
+    if (const char* v = std::getenv("SDVG_LN_FOLD_MIN")) fold_min_rows = std::atoi(v);   // (tests: fold at any size)
+    if (use_fold && tc() && !split_all() && d % 64 == 0 && max_rows >= fold_min_rows) {
+      // every projection that reads a LayerNorm output gets gamma-scaled planes of its own (C2: +0.47 GB)
+      fold_ld = 2 * ceil_div(d, 64);     // column slots per row: two epilogue warps per tile, tiles at least 64 wide
+      if ((e = dalloc(&ln_part, static_cast<size_t>(max_rows) * fold_ld)) != cudaSuccess) return fail_cuda(e, "fold partials alloc");
+      auto add_fold = [&](Linear& L, const LNParam& norm) -> bool {
+        if (L.split) return true;
+        if (alloc_planes(L.pf, L.N, L.K, false, true) != cudaSuccess || dalloc(&L.fold_c, static_cast<size_t>(L.N)) != cudaSuccess ||
+            dalloc(&L.fold_b, static_cast<size_t>(L.N)) != cudaSuccess || !map_planes(L.pf, true))
+          return false;
+        L.fold_norm = norm; L.has_fold = true;
+        return true;
+      };
+      bool okf = true;
+      for (size_t l = 0; l < enc.size() && okf; ++l) {
+        okf = add_fold(enc[l].ff1, enc[l].n1);
+        if (l > 0 && okf) okf = add_fold(enc[l].sa.qkv, enc[l - 1].n2);
+      }
+      for (size_t l = 0; l < dec.size() && okf; ++l) {
+        okf = add_fold(dec[l].ca.q, dec[l].n1) && add_fold(dec[l].ff1, dec[l].n2);
+        if (l > 0 && okf) okf = add_fold(dec[l].sa.qkv, dec[l - 1].n3);
+      }
+      if (!okf) return fail(SDVG_ERR_CUDA, "allocation of the LayerNorm-folded weight planes failed");
+    } else {
+      use_fold = false;
+    }
     std::vector<int> mod(c.max_clips);
     for (int i = 0; i < c.max_clips; ++i) mod[i] = i % 64;
     if ((e = dalloc(&pe_mod64, static_cast<size_t>(c.max_clips))) != cudaSuccess) return fail_cuda(e, "pe alloc");
@@ -503,6 +545,20 @@ class Engine {
     return cudaSuccess;
   }
 
+  // (re)build the gamma-scaled planes, their row sums and folded biases from the current fp32 parameters
+  cudaError_t refold(cudaStream_t st) {
+    if (!use_fold) return cudaSuccess;
+    auto one = [&](Linear& L) -> cudaError_t {
+      if (!L.has_fold) return cudaSuccess;
+      ++launches;
+      return launch_kernel(ln_fold_weights_kernel, dim3(L.N), dim3(128), 0, st, L.w32, L.K, L.pf.ld, L.bias, L.fold_norm.w,
+                           L.fold_norm.b, L.pf.hi, L.fold_c, L.fold_b, bf16() ? 1 : 0);
+    };
+    for (auto& l : enc) { SDVG_CK(one(l.ff1)); SDVG_CK(one(l.sa.qkv)); }
+    for (auto& l : dec) { SDVG_CK(one(l.ca.q)); SDVG_CK(one(l.ff1)); SDVG_CK(one(l.sa.qkv)); }
+    return cudaSuccess;
+  }
+
   int finalize(cudaStream_t st) {
     if (finalized) return SDVG_OK;
     for (auto& s : slots)
@@ -521,6 +577,7 @@ class Engine {
       }
     }
     cudaError_t e = restack_cross(st);
+    if (e == cudaSuccess) e = refold(st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail_cuda(e, "finalize sync");
     finalized = true;
@@ -699,10 +756,19 @@ class Engine {
     }
     const bool split = L.split && A.p.lo != nullptr;
     const TilePlan plan = (use_ksplit && M <= kTcBM && L.K > 256) ? choose_small_m(M, L.N, L.K, split) : choose_plan(M, L.N, split, L.K);
+    if (e.ln_in) {   // A holds pre-norm sums: gamma-scaled planes, c in place of the deferred-LayerNorm weights, b' as the bias
+      if (!L.has_fold || split) return cudaErrorInvalidValue;
+      e.ln_w = L.fold_c; e.ln_b = L.fold_c; e.bias = L.fold_b;
+    }
+    if (e.stat_out) {
+      if (plan.ks > 1 || !epilogue_vec4_ok(e, L.N)) return cudaErrorInvalidValue;
+      last_stat_slots = ceil_div(L.N, plan.bn) * ((plan.pair || plan.bn >= 64) ? 2 : 1);
+      if (last_stat_slots > e.stat_ld) return cudaErrorInvalidValue;
+    }
     TcGemmArgs args{M, L.N, L.K, bf16() ? 1 : 0, 0, kTcBM, 0, nullptr, e};
     const double planes = split ? 2.0 : 1.0;
     Scope sc(this, KC_GEMM_TC, flops, 2.0 * planes * (double(M) * L.K + double(L.N) * L.K) + 4.0 * double(M) * L.N, st);
-    return gemm_tc_dispatch(A.p, L.p, split, plan, args, st);
+    return gemm_tc_dispatch(A.p, e.ln_in ? L.pf : L.p, split, plan, args, st);
   }
 
   // destination description shared by LN / attention / GEMM epilogues
@@ -1087,10 +1153,16 @@ class Engine {
   // LayerNorm that turned them into the current stream - the consuming GEMM epilogue recomputes LayerNorm(y) for
   // the elements it adds, so that LayerNorm kernel only writes the 16-bit operand planes and 8 bytes per row
   // instead of a second fp32 copy of the stream (LayerNorm was HBM-bound: 10 -> 6 bytes per element).
+  // Folded (fold == true, implies deferred): no LayerNorm kernel ran at all - the stream's operand planes hold the
+  // PRE-norm sums as well, and the projections that read them use their gamma-scaled weights (Epilogue::ln_in).
   struct ResSrc {
     const float* ptr = nullptr; int ld = 0;
     const float2* stats = nullptr; const float* w = nullptr; const float* b = nullptr;
+    bool fold = false;
   };
+  static void operand_from(Epilogue& e, const ResSrc& rs) {
+    if (rs.fold) { e.ln_in = 1; e.ln_stats = rs.stats; }
+  }
   static void residual_from(Epilogue& e, const ResSrc& rs) {
     e.residual = rs.ptr; e.ld_res = rs.ld; e.ln_stats = rs.stats; e.ln_w = rs.w; e.ln_b = rs.b;
   }
@@ -1111,7 +1183,19 @@ class Engine {
     const int hd = d / cfg.num_heads;
     const bool lazy = lazy_ln && tc();
     // LayerNorm of ybuf into the stream buffer `x_out`; returns how the next sub-layer reads its residual
+    // LayerNorm folded away: decided BEFORE the producing GEMM (which then also writes the pre-norm planes and the row
+    // partials); norm_to() only turns the partials into (mean, rstd)
+    auto fold_here = [&](int M, bool allow_lazy) { return use_fold && lazy && allow_lazy && !pk_rec && M >= fold_min_rows; };
+    auto fold_outputs = [&](Epilogue& e, const ActBuf& x_out) {
+      e.out_hi = x_out.p.hi; e.out_lo = nullptr; e.ld16 = x_out.p.ld;
+      e.stat_out = ln_part; e.stat_ld = fold_ld;
+    };
     auto norm_to = [&](int M, int S, const LNParam& norm, const ActBuf& x_out, bool allow_lazy, ResSrc& out_rs) -> cudaError_t {
+      if (fold_here(M, allow_lazy)) {
+        out_rs = ResSrc{ybuf.f32, ybuf.ld32, ln_stats, norm.w, norm.b, true};
+        Scope sc(this, KC_LN, 0.0, double(M) * last_stat_slots * 8.0, st);
+        return launch_ln_stats_finalize(ln_part, fold_ld, last_stat_slots, M, d, cfg.layer_norm_eps, ln_stats, st);
+      }
       if (lazy && allow_lazy) {
         out_rs = ResSrc{ybuf.f32, ybuf.ld32, ln_stats, norm.w, norm.b};
         return layernorm(ybuf, M, norm, nullptr, x_out, false, S, 0, st, ln_stats);
@@ -1122,6 +1206,7 @@ class Engine {
     auto self_attention = [&](const ActBuf& x, ResSrc& rs, const AttnWeights& w, int S, int M, int mk, const float* mptr,
                               const LNParam& norm, const ActBuf& x_out, bool first_layer, bool allow_lazy) -> cudaError_t {
       Epilogue e;
+      operand_from(e, rs);
       if (qkv16 && !first_layer && attention16_supported(hd, S, S, mk)) {
         e.out_hi = qkv16; e.ld16 = 3 * d;   // Q|K|V straight to 16-bit planes
         SDVG_CK(gemm(x, w.qkv, M, e, st));
@@ -1136,6 +1221,7 @@ class Engine {
       Epilogue eo;
       residual_from(eo, rs);
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+      if (fold_here(M, allow_lazy)) fold_outputs(eo, x_out);
       SDVG_CK(gemm(attn, w.out, M, eo, st));
       return norm_to(M, S, norm, x_out, allow_lazy, rs);
     };
@@ -1144,10 +1230,12 @@ class Engine {
       Epilogue e1;
       e1.relu = 1;
       out_to(e1, ffh, !tc());
+      operand_from(e1, rs);
       SDVG_CK(gemm(x, l1, M, e1, st));
       Epilogue e2;
       residual_from(e2, rs);
       out_to(e2, ybuf, true); e2.out_hi = nullptr; e2.out_lo = nullptr;
+      if (!chained && fold_here(M, allow_lazy)) fold_outputs(e2, x_out);
       SDVG_CK(gemm(ffh, l2, M, e2, st));
       if (chained) {  // last layer of a stack: norm chained with the stack's final norm, operand planes only
         rs = ResSrc{};
@@ -1170,6 +1258,7 @@ class Engine {
       Epilogue eo;
       eo.residual = c_emb; eo.ld_res = d; eo.rows_per_clip = S; eo.res_clip_rows = cs->Hn; eo.res_row_off = cs->first;
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+      if (fold_here(M, true)) fold_outputs(eo, x_out);
       SDVG_CK(gemm(attn, w.out, M, eo, st));
       return norm_to(M, S, norm, x_out, true, rs);
     };
@@ -1229,6 +1318,7 @@ class Engine {
       else SDVG_CK(self_attention(*y, rs, dec[l].sa, St, Mt, mask_kind, mask, dec[l].n1, xt, l == 0, true));
       // cross attention: Q from the target stream, K/V from the encoder memory
       Epilogue eq, ekv;
+      operand_from(eq, rs);
       if (cross_batched) {
         eq.out_hi = qc16; eq.ld16 = d;
         SDVG_CK(gemm(xt, dec[l].ca.q, Mt, eq, st));
@@ -1252,6 +1342,7 @@ class Engine {
       Epilogue eo;
       residual_from(eo, rs);
       out_to(eo, ybuf, true); eo.out_hi = nullptr; eo.out_lo = nullptr;
+      if (fold_here(Mt, true)) fold_outputs(eo, xt);
       SDVG_CK(gemm(attn, dec[l].ca.out, Mt, eo, st));
       SDVG_CK(norm_to(Mt, St, dec[l].n2, xt, true, rs));
       const bool last = (l == Ld - 1);

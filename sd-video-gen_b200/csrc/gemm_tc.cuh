@@ -273,6 +273,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
   const size_t ld32 = e.ld32, ld16 = e.ld16;
   const uint32_t rd_addr = stg_addr + (lr * kTcEpiStride + lc) * 4;
   const uint32_t wr_addr = stg_addr + lane * kTcEpiStride * 4;
+  const bool ln_in = e.ln_in != 0;
+  float2* const stat_out = e.stat_out;
+  float ssum[8], ssq[8];   // producer of a folded LayerNorm: this lane's share of (sum, sum of squares) of its 8 rows
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
 
 #pragma unroll
   for (int j = 0; j < NCW; ++j) {
@@ -311,6 +316,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
         float4 v = lds128(rd_addr + i * 4 * kTcEpiStride * 4);
         if (rr < rows_valid) {
           const int row = row0 + rr;
+          if (ln_in) {   // LayerNorm folded into this GEMM: lw = row sums of the gamma-scaled weight planes
+            const float2 st = pre.st[i];
+            v.x = st.y * (v.x - st.x * lw.x); v.y = st.y * (v.y - st.x * lw.y);
+            v.z = st.y * (v.z - st.x * lw.z); v.w = st.y * (v.w - st.x * lw.w);
+          }
           v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           int out_row = row;
           if constexpr (FANCY) {
@@ -354,6 +364,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
             }
             v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
           }
+          if (stat_out) {
+            ssum[i] += (v.x + v.y) + (v.z + v.w);
+            ssq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+          }
           if (out32 && out_row >= 0) *reinterpret_cast<float4*>(out32 + static_cast<size_t>(out_row) * ld32 + col) = v;
           if (out_hi) {
             const uint2 h = pack_hi4(v, bf16);
@@ -369,6 +383,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
       epi_prefetch_chunk<FANCY>(args, row0, col_base + (c + PF) * 32 + lc, lr, pre.b4[j % PF], pre.res[j % PF],
                                 pre.lw[j % PF], pre.lb[j % PF]);
     __syncwarp();
+  }
+  if (stat_out) {
+    // the 8 lanes that share a row (lr fixed, lc = 0..28) add up their parts; slot = this warp's position along N
+    constexpr int kSlotsPerTile = (BN / 32) / NCW;
+    const int slot = (col_base / BN) * kSlotsPerTile + c0 / NCW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = ssum[i], q = ssq[i];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+      const int rr = i * 4 + lr;
+      if ((lane & 7) == 0 && rr < rows_valid) stat_out[static_cast<size_t>(row0 + rr) * e.stat_ld + slot] = make_float2(s, q);
+    }
   }
 }
 

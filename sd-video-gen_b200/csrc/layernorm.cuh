@@ -183,6 +183,68 @@ __global__ void __launch_bounds__(128) layernorm_block_kernel(const __grid_const
   }
 }
 
+// ---- LayerNorm folded into the neighbouring GEMMs (Epilogue::ln_in / stat_out, common.cuh) ---------------------------
+// Row statistics from the partial sums the producing GEMM's epilogue warps left behind: one thread per row adds its
+// `slots` partials in a fixed order (deterministic), biased variance as E[y^2] - mean^2 (16-bit modes only: the rows are
+// post-norm residual sums, |mean| <~ std, so the cancellation costs a few ulps of fp32).
+__global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ part, int ld, int slots, int rows, float inv_d,
+                                                                float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  // one warp per row: lane i takes slots i, i + 32, ...; fixed-shape butterfly sum (deterministic).  (First version: one
+  // thread per row walking its 22 slots - 20 blocks of serialised L2 round trips, 28 us per launch.)
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float2* p = part + static_cast<size_t>(r) * ld;
+  float s = 0.f, q = 0.f;
+  for (int i = lane; i < slots; i += 32) { const float2 v = __ldcg(p + i); s += v.x; q += v.y; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane == 0) {
+    const float mean = s * inv_d;
+    const float var = fmaxf(q * inv_d - mean * mean, 0.f);
+    stats[r] = make_float2(mean, rsqrtf(var + eps));
+  }
+}
+inline cudaError_t launch_ln_stats_finalize(const float2* part, int ld, int slots, int rows, int d, float eps, float2* stats,
+                                            cudaStream_t stream) {
+  return launch_kernel(ln_stats_finalize_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, part, ld, slots, rows,
+                       1.0f / static_cast<float>(d), eps, stats);
+}
+
+// Weight planes of a GEMM that consumes LayerNorm(y) directly from y: W' = W diag(gamma) in the operand format, with
+// c[n] = sum_k W'[n][k] (of the ROUNDED plane values, so that the mean term cancels exactly as the tensor cores see it)
+// and b'[n] = b[n] + sum_k beta[k] W[n][k].  One block per weight row; runs when the weights change, not per step.
+__global__ void __launch_bounds__(128) ln_fold_weights_kernel(const float* __restrict__ w, int K, int ld16, const float* __restrict__ bias,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              uint16_t* __restrict__ hi, float* __restrict__ c, float* __restrict__ bfold,
+                                                              int bf16) {
+  __shared__ float red[8];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float* wr = w + static_cast<size_t>(n) * K;
+  uint16_t* hr = hi + static_cast<size_t>(n) * ld16;
+  float cs = 0.f, bs = 0.f;
+  for (int k = tid; k < ld16; k += 128) {
+    uint16_t h = 0;
+    if (k < K) {
+      const float wv = wr[k];
+      h = to_plane_hi(wv * gamma[k], bf16);
+      cs += bf16 ? __bfloat162float(__ushort_as_bfloat16(h)) : __half2float(__ushort_as_half(h));
+      bs = fmaf(beta[k], wv, bs);
+    }
+    hr[k] = h;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, o); bs += __shfl_xor_sync(0xffffffffu, bs, o); }
+  if ((tid & 31) == 0) { red[tid >> 5] = cs; red[4 + (tid >> 5)] = bs; }
+  __syncthreads();
+  if (tid == 0) {
+    c[n] = (red[0] + red[1]) + (red[2] + red[3]);
+    bfold[n] = bias[n] + ((red[4] + red[5]) + (red[6] + red[7]));
+  }
+}
+
 inline cudaError_t launch_layernorm(const LnArgs& a, cudaStream_t stream) {
   if (a.d % 4 != 0 || a.d > 4096) return cudaErrorInvalidValue;
   const int keep = a.rows_per_clip - a.first_token;

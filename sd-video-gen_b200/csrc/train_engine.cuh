@@ -281,7 +281,10 @@ class Trainer {
     }
     if (lo == 0) {   // a full rebuild, or the last range of a ranged one (ranges run from the end of the arena to its start)
       wt_stale = false;
-      if (forward_planes) SDVG_CK(g.restack_cross(st));   // the rollout path's stacked cross-attention operand follows the weights
+      if (forward_planes) {   // the rollout path's derived operands follow the weights: stacked cross-attention K|V, folded LayerNorms
+        SDVG_CK(g.restack_cross(st));
+        SDVG_CK(g.refold(st));
+      }
     }
     return cudaSuccess;
   }

@@ -369,6 +369,9 @@ def test_last_layer_pruning_is_exact(monkeypatch):
     g = load_golden("small_rollout")
     ctx = torch.randn(70, 7, 256, generator=torch.Generator().manual_seed(18)).to(DEV)
     outs = {}
+    # (the layer that feeds the pruned one keeps a LayerNorm kernel where the unpruned model folds it into the GEMMs: with
+    # folding the two runs differ by 16-bit rounding, not by the pruning - keep it out of this comparison)
+    monkeypatch.setenv("SDVG_LN_FOLD", "0")
     for flag in ("0", "1"):
         monkeypatch.setenv("SDVG_PRUNE", flag)
         for prec in ("fp32", "mixed"):
@@ -469,3 +472,31 @@ def test_rollout_from_the_npy_latent_cache(tmp_path):
     assert torch.equal(ctx, g["ctx"])
     out = sdvg_b200.rollout_from_host(m, ctx, 4, 5)
     assert R.max_rel_per_frame(out, g["free5"]).max() < TOL32
+
+
+def test_layernorm_folded_into_the_gemms(monkeypatch):
+    """Large batches in the 16-bit modes run without LayerNorm kernels between the sub-layers: the producing GEMM's
+    epilogue leaves per-row partial sums, the consuming GEMM reads the pre-norm sums through gamma-scaled weights and
+    applies rstd * (acc - mean * c) + b' (Engine::fold_*, SDVG_LN_FOLD).  Forced on at any batch size here: the golden
+    forward / rollout values of the reference within the 16-bit tolerance, agreement with the unfolded path at rounding
+    level, and no effect on the fp32 mode (never folded)."""
+    g = load_golden("small_rollout")
+    ctx = g["ctx"].to(DEV)
+    n = g["free5"].shape[1]
+    outs = {}
+    for fold in ("0", "1"):
+        monkeypatch.setenv("SDVG_LN_FOLD", fold)
+        monkeypatch.setenv("SDVG_LN_FOLD_MIN", "1")
+        for prec in ("mixed", "fp16", "bf16", "fp32"):
+            m, _ = ours_from(g, prec)
+            tf = sdvg_b200.rollout(m, ctx, n, 5, teacher=g["free5"].to(DEV)).cpu()
+            outs[fold, prec] = tf
+            tol = {"fp32": TOL32, "bf16": 4e-2}.get(prec, TOL16)
+            assert R.max_rel_per_frame(tf, g["free5"]).max() < tol, (fold, prec)
+            big = torch.randn(130, 6, 256, generator=torch.Generator().manual_seed(7)).to(DEV)       # several row tiles, B > 64
+            pe = (torch.arange(130) % 64).to(torch.int32).to(DEV)
+            outs[fold, prec, "big"] = sdvg_b200.rollout(m, big, 2, 5, pe_index=pe).cpu()
+    assert torch.equal(outs["0", "fp32"], outs["1", "fp32"])
+    for prec in ("mixed", "fp16"):
+        assert not torch.equal(outs["0", prec], outs["1", prec])                         # the folded path really ran
+        assert R.max_rel_per_frame(outs["1", prec, "big"], outs["0", prec, "big"])[0] < TOL16
