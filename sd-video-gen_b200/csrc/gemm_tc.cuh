@@ -39,7 +39,7 @@ struct TcCfg {
   static constexpr int kABytes = kTcBM * kTcBK * 2;
   static constexpr int kBBytes = BN * kTcBK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4;
+  static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4 + kTcEpiWarps * 32 * 8;   // transpose tiles + (mean, rstd) of each warp's 32 rows
   // epilogue warps that take part: two per quadrant split the tile's 32-column chunks (one per quadrant if BN == 32)
   static constexpr int kEpiActive = BN >= 64 ? 8 : 4;
   static constexpr int kBarBytes = 1024;
@@ -119,7 +119,8 @@ struct EpiPre {
   float4 b4[PF];
   float4 res[PF][8];
   float4 lw[PF], lb[PF];  // deferred-LayerNorm weights of the chunk's columns (Epilogue::ln_stats mode)
-  float2 st[8];           // (mean, rstd) of this lane's 8 rows of the tile
+  float2* st;             // shared memory, [32]: (mean, rstd) of the warp's 32 rows (16 registers per thread when it was an
+                          // array here: the epilogue is at the register limit and spilled once the folded LayerNorm came in)
 };
 
 template <bool FANCY>
@@ -154,13 +155,11 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmArgs& args, int
   if (!args.vec4) return;
   const int lr = lane >> 3, lc = (lane & 7) * 4;
   if (args.epi.ln_stats) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + i * 4 + lr;
-      int rrow = row;
-      if constexpr (FANCY) rrow = epi_res_row(args.epi, row);
-      pre.st[i] = row < args.M ? __ldg(args.epi.ln_stats + rrow) : make_float2(0.f, 0.f);
-    }
+    const int row = row0 + lane;
+    int rrow = row;
+    if constexpr (FANCY) rrow = epi_res_row(args.epi, row);
+    pre.st[lane] = row < args.M ? __ldg(args.epi.ln_stats + rrow) : make_float2(0.f, 0.f);
+    __syncwarp();
   }
 #pragma unroll
   for (int j = 0; j < (NCW < PF ? NCW : PF); ++j)
@@ -317,7 +316,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
         if (rr < rows_valid) {
           const int row = row0 + rr;
           if (ln_in) {   // LayerNorm folded into this GEMM: lw = row sums of the gamma-scaled weight planes
-            const float2 st = pre.st[i];
+            const float2 st = pre.st[i * 4 + lr];
             v.x = st.y * (v.x - st.x * lw.x); v.y = st.y * (v.y - st.x * lw.y);
             v.z = st.y * (v.z - st.x * lw.z); v.w = st.y * (v.w - st.x * lw.w);
           }
@@ -358,7 +357,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmArgs& args, float* 
           if (residual) {
             float4 rv = pre.res[j % PF][i];
             if (ln_res) {  // LayerNorm of the pre-norm sums, recomputed from the row statistics
-              const float2 st = pre.st[i];
+              const float2 st = pre.st[i * 4 + lr];
               rv.x = (rv.x - st.x) * st.y * lw.x + lb.x; rv.y = (rv.y - st.x) * st.y * lw.y + lb.y;
               rv.z = (rv.z - st.x) * st.y * lw.z + lb.z; rv.w = (rv.w - st.x) * st.y * lw.w + lb.w;
             }
@@ -556,6 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         continue;
       }
       EpiPre<PF> pre;
+      pre.st = reinterpret_cast<float2*>(epi_stage + kTcEpiWarps * 32 * kTcEpiStride) + (warp - 2) * 32;
       tc_epilogue_prefetch<FANCY, NCW, PF>(args, row0, n_blk * BN, lane, c0, pre);
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();

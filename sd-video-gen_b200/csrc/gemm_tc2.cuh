@@ -33,7 +33,7 @@ struct Tc2Cfg {
   static constexpr int kBRows = BN / 2;                    // this CTA's half of the W tile
   static constexpr int kBBytes = kBRows * kTcBK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4;
+  static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4 + kTcEpiWarps * 32 * 8;   // transpose tiles + (mean, rstd) of each warp's 32 rows
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxStages = (kTcSmemLimit - 1024 - kEpiBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -194,6 +194,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int n_blk = t / m_tiles, m_blk = t - n_blk * m_tiles;
       const int row0 = m_blk * kTc2BM + static_cast<int>(rank) * kTcBM + q * 32;
       EpiPre<PF> pre;
+      pre.st = reinterpret_cast<float2*>(epi_stage + kTcEpiWarps * 32 * kTcEpiStride) + (warp - 2) * 32;
       tc_epilogue_prefetch<FANCY, NCW, PF>(args, row0, n_blk * BN, lane, c0, pre);   // in flight during the main loop
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
