@@ -59,8 +59,9 @@ def main():
         "kernel": "sdvg::gemm_tc2_kernel<192,false,false> M=5120 N=2048 K=2048 (52 of 74 GEMM launches per model pass)",
         "git_head": head, "kernel_sources": SOURCES, "kernel_sources_sha256": h.hexdigest(),
         "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": rd + wr,
-        # A planes 2 B + W planes 2 B + fp32 residual in + fp32 out (out-proj / FF2; DESIGN.md kernel table)
-        "algorithmic_bytes_per_launch": 2 * M * K + 2 * N * K + 4 * M * N + 4 * M * N,
+        # A planes 2 B + W planes 2 B + fp32 residual in + fp32 out + 16-bit planes of the pre-norm sums (out-proj / FF2
+        # with the LayerNorm folded in; DESIGN.md kernel table)
+        "algorithmic_bytes_per_launch": 2 * M * K + 2 * N * K + 4 * M * N + 4 * M * N + 2 * M * N,
         "tensor_pipe_active_pct": sum(float(r[idx["sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"]]) for r in big) / len(big),
         "duration_us": sum(float(r[idx["gpu__time_duration.sum"]]) for r in big) / len(big),
     }
