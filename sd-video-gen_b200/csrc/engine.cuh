@@ -138,7 +138,7 @@ class Engine {
   // LayerNorm folded into the neighbouring GEMMs at large batch (SDVG_LN_FOLD, 16-bit non-split modes): the producer's
   // epilogue leaves per-row partial sums in ln_part, the consumer reads the pre-norm planes through gamma-scaled weights
   bool use_fold = true;        // SDVG_LN_FOLD=0 disables (same-box A/B on B200: 50.0 -> 48.2 ms per C2 step, profiles/README.md round 2)
-  int fold_min_rows = 512;
+  int fold_min_rows = 1;       // (SDVG_LN_FOLD_MIN) also pays at small batch: C1 launch chain 872 -> 845 us per pass
   float2* ln_part = nullptr;   // [max_rows][fold_ld]
   int fold_ld = 0;
   int last_stat_slots = 0;     // column slots the last stat_out GEMM wrote per row (depends on its tile plan)
