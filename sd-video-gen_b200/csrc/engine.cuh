@@ -33,6 +33,8 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 constexpr int kNumBoxes = 5;
 constexpr int kBoxRows[kNumBoxes] = {32, 64, 96, 128, 256};
 inline int box_index(int rows) { return rows == 32 ? 0 : rows == 64 ? 1 : rows == 96 ? 2 : rows == 128 ? 3 : 4; }
+// activation planes: box heights of the A operand by slot (one-CTA kernel; multiples of the 8-row swizzle atom)
+constexpr int kActBoxRows[kNumBoxes] = {128, 64, 48, 32, 16};
 
 // A GEMM tile plan: pair = CTA-pair kernel (256 x bn tiles) or one-CTA kernel (128 x bn tiles).
 struct TilePlan { bool pair; int bn; int ks = 1; };
@@ -250,10 +252,10 @@ class Engine {
   bool map_planes(Planes& p, bool weight) {
     // lo planes are always fp16; hi planes follow the mode
     if (!weight) {
-      // slot 0: 128-row boxes (the tile height); slots 1, 2: 64- and 32-row boxes for small-M GEMMs, which
-      // would otherwise stream 128 rows of A per K block to use 40 of them (a_box_slot)
-      for (int s = 0; s < 3; ++s) {
-        const int box = kTcBM >> s;
+      // slot 0: 128-row boxes (the tile height); slots 1..4: 64-, 48-, 32- and 16-row boxes for small-M GEMMs, which
+      // would otherwise stream 128 rows of A per K block to use 40 (8 clips x 5 tokens) or 5 (batch 1) of them (a_box_slot)
+      for (int s = 0; s < kNumBoxes; ++s) {
+        const int box = kActBoxRows[s];
         if (!make_tmap_2d(&p.tm_hi[s], p.hi, p.rows, p.cols, p.ld, box, bf16())) return false;
         if (p.lo && !make_tmap_2d(&p.tm_lo[s], p.lo, p.rows, p.cols, p.ld, box, false)) return false;
       }
@@ -681,7 +683,7 @@ class Engine {
   TilePlan choose_small_m(int M, int N, int K, bool split) const {
     const int nk = ceil_div(K, kTcBK);
     const int planes = split ? 2 : 1;
-    const int a_rows = kTcBM >> a_box_slot(M);
+    const int a_rows = kActBoxRows[a_box_slot(M)];
     TilePlan best{false, 32, 1};
     double best_cost = 1e300;
     for (int bn : {32, 64, 128}) {
@@ -704,12 +706,12 @@ class Engine {
   }
 
   // A-operand TMA box height for the one-CTA kernel: 128 rows, or 64 / 32 when the whole problem has fewer rows
-  static int a_box_slot(int M) { return M <= 32 ? 2 : M <= 64 ? 1 : 0; }
+  static int a_box_slot(int M) { return M <= 16 ? 4 : M <= 32 ? 3 : M <= 48 ? 2 : M <= 64 ? 1 : 0; }
 
   cudaError_t gemm_tc_dispatch(const Planes& A, const Planes& B, bool split, TilePlan plan, const TcGemmArgs& args_in,
                                cudaStream_t st) {
     TcGemmArgs args = args_in;
-    args.a_box_rows = plan.pair ? kTcBM : (kTcBM >> a_box_slot(args.M));
+    args.a_box_rows = plan.pair ? kTcBM : kActBoxRows[a_box_slot(args.M)];
     if (!plan.pair && plan.ks > 1) { args.ksplit = plan.ks; if (!args.ks_ws) { args.ks_ws = ks_ws; args.ks_flags = ks_flags; } }
     const int bn = plan.bn;
     const int bi = box_index(plan.pair ? bn / 2 : bn);

@@ -337,9 +337,9 @@ int sdvg_gemm(int32_t device, int32_t precision, const float* A, const float* W,
     const int bi = box_index(plan.pair ? bn / 2 : bn);
     ok = make_tmap_2d(&pb.tm_hi[bi], w_hi, N, Kp, Kp, box, bf);
     if (ok && split) ok = make_tmap_2d(&pb.tm_lo[bi], w_lo, N, Kp, Kp, box, false);
-    for (int s = 0; s < 3 && ok; ++s) {
-      ok = make_tmap_2d(&pa.tm_hi[s], a_hi, Mp, Kp, Kp, kTcBM >> s, bf);
-      if (ok && split) ok = make_tmap_2d(&pa.tm_lo[s], a_lo, Mp, Kp, Kp, kTcBM >> s, false);
+    for (int s = 0; s < kNumBoxes && ok; ++s) {
+      ok = make_tmap_2d(&pa.tm_hi[s], a_hi, Mp, Kp, Kp, kActBoxRows[s], bf);
+      if (ok && split) ok = make_tmap_2d(&pa.tm_lo[s], a_lo, Mp, Kp, Kp, kActBoxRows[s], false);
     }
     if (!ok) { cleanup(); g_create_error = "sdvg_gemm: cuTensorMapEncodeTiled failed"; return SDVG_ERR_CUDA; }
     TcGemmArgs args{M, N, K, bf ? 1 : 0, 0, kTcBM, 0, nullptr, e};

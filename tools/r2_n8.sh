@@ -1,0 +1,2 @@
+set -x
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_r2_n8.json 2>gpurun_out/bench_r2_n8.err
