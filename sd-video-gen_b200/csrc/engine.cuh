@@ -1008,9 +1008,10 @@ class Engine {
           const unsigned long long g0 = h[static_cast<size_t>(i) * 32 + 5], g1 = h[static_cast<size_t>(i) * 32 + 12];
           if (g1 > g0) std::fprintf(stderr, " | SM clock %.0f MHz", double(c1 - c0) / double(g1 - g0) * 1e3);
           std::fprintf(stderr, "\n        fine: mma-blocks");
-          for (int e = 16; e < 23; ++e) {
+          for (int e = 16; e < 25; ++e) {
             const unsigned long long v = h[static_cast<size_t>(i) * 32 + e];
             if (e == 20) std::fprintf(stderr, " | A-issued setup a_empty");
+            if (e == 23) std::fprintf(stderr, " | copies issued landed");
             if (v) std::fprintf(stderr, " %7llu", v - t0); else std::fprintf(stderr, "       -");
           }
           std::fprintf(stderr, "\n");

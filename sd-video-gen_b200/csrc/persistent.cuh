@@ -48,6 +48,7 @@ constexpr int kPkRpo = 16;                             // token rows per owner C
 constexpr int kPkGroup = kPkCluster * kPkRpo;          // tokens per exchange group (64)
 constexpr int kPkRedBytes = kPkCluster * kPkTileN * kPkRpo * 4;   // partial tiles received from the 4 sources (32 KB)
 constexpr long long kPkSpinLimit = 4000000000LL;
+constexpr int kPkChunk = 4;                            // weight-slot groups the MMA warp awaits and issues as one batch
 
 enum PkType : int { PK_GEMM = 1, PK_LN = 2, PK_ATTN = 3, PK_PACK = 4, PK_ADD = 5 };
 
@@ -160,20 +161,19 @@ __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t
       : "memory");
 }
 // the four K = 16 steps of one 64-column block (operand start addresses advance by 32 bytes = 2 descriptor units)
-// Even and odd K steps accumulate into two different TMEM accumulators (mtp columns apart; summed when the partial is
-// staged): with 48-column tiles an MMA is shorter than the tensor pipe is deep, and a single accumulator made the 32
-// MMAs of a tile one dependent chain.
+// One accumulator per term: tools/mma_rate.cu measures 48 cycles per 128 x (<= 64) x 16 MMA whether the MMAs of a tile
+// accumulate into one, two or four TMEM regions (the first version alternated even / odd K steps between two
+// accumulators and paid two more TMEM loads per staged block for it).
 template <bool SPLIT>
 __device__ __forceinline__ void mma_block(uint32_t d0, uint32_t d1, uint32_t mtp, uint32_t w_hi, uint32_t w_lo, uint32_t a_hi, uint32_t a_lo,
                                           uint32_t idesc, bool first) {
 #pragma unroll
   for (int k = 0; k < kTcBK / 16; ++k) {
-    const uint32_t acc = (!first || k >= 2) ? 1u : 0u;
-    const uint32_t o = (k & 1) ? mtp : 0u;
-    umma_lo(d0 + o, w_hi + 2 * k, a_hi + 2 * k, idesc, acc);
+    const uint32_t acc = (!first || k >= 1) ? 1u : 0u;
+    umma_lo(d0, w_hi + 2 * k, a_hi + 2 * k, idesc, acc);
     if (SPLIT) {   // split modes use fp16 hi planes, lo planes are always fp16: one instruction descriptor
-      umma_lo(d1 + o, w_hi + 2 * k, a_lo + 2 * k, idesc, acc);
-      umma_lo(d1 + o, w_lo + 2 * k, a_hi + 2 * k, idesc, 1u);
+      umma_lo(d1, w_hi + 2 * k, a_lo + 2 * k, idesc, acc);
+      umma_lo(d1, w_lo + 2 * k, a_hi + 2 * k, idesc, 1u);
     }
   }
 }
@@ -238,6 +238,9 @@ __device__ __forceinline__ void load_a_block(const APieces& ap, long long plane_
 template <int NP>
 __device__ __forceinline__ void issue_slab(const APieces& ap, long long lo_off, bool split, int kb0, int kb1, int s, int a_stages,
                                            uint32_t a_ring_addr, uint32_t a_stage_bytes) {
+  // (unrolled: one LDGSTS holds its address registers until the load/store unit has read them - with one K block per
+  // loop iteration every iteration waited ~190 cycles for the previous block's copies to release theirs: 0.8 us per slab)
+#pragma unroll 4
   for (int kb = kb0; kb < kb1; ++kb) {
     load_a_block<NP>(ap, 0, kb, a_ring_addr + static_cast<uint32_t>(s) * a_stage_bytes);
     if (++s == a_stages) s = 0;
@@ -249,6 +252,9 @@ __device__ __forceinline__ void issue_slab(const APieces& ap, long long lo_off, 
 }
 // (separate from the copies: ARRIVES.LDGSTSBAR holds the warp until its outstanding copies have landed - signalling
 // after every block serialised the slab into one L2 round trip per block)
+__device__ __forceinline__ void mbar_arrive_count(uint32_t bar_addr, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(count) : "memory");
+}
 __device__ __forceinline__ void a_block_arrive(uint32_t bar_addr) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
@@ -264,22 +270,15 @@ __device__ __forceinline__ void stage_partial(uint32_t tacc, uint32_t mtp, bool 
   for (int r = 0; r < kPkCluster; ++r)
     if (r < owners) tmem_ld_x16(tacc + tok0 + r * kPkRpo, v[r]);
   ptx::tmem_ld_wait();
+  if (split) {
 #pragma unroll
-  for (int r = 0; r < kPkCluster; ++r) {
-    if (r < owners) {
-      uint32_t w[16];
-      tmem_ld_x16(tacc + mtp + tok0 + r * kPkRpo, w);          // odd K steps
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[r][j] = __float_as_uint(__uint_as_float(v[r][j]) + __uint_as_float(w[j]));
-      if (split) {
-        uint32_t x[16];
+    for (int r = 0; r < kPkCluster; ++r) {
+      if (r < owners) {
+        uint32_t w[16];
         tmem_ld_x16(tacc + 2 * mtp + tok0 + r * kPkRpo, w);    // cross terms, kept scaled by 2^11
-        tmem_ld_x16(tacc + 3 * mtp + tok0 + r * kPkRpo, x);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[r][j] = __float_as_uint(fmaf(__uint_as_float(w[j]) + __uint_as_float(x[j]), kSplitInv, __uint_as_float(v[r][j])));
+        for (int j = 0; j < 16; ++j) v[r][j] = __float_as_uint(fmaf(__uint_as_float(w[j]), kSplitInv, __uint_as_float(v[r][j])));
       }
     }
   }
@@ -835,40 +834,98 @@ persistent_kernel(const __grid_constant__ PkParams P) {
           ptx::fence_proxy_async_smem();
           ptx::tc_fence_after();
         }
-        for (int kb = kb0; kb < kb1; kb += cps) {
-          const int nb = kb1 - kb < cps ? kb1 - kb : cps;
-          const int ws1 = (ws + 1 == P.w_slots) ? 0 : ws + 1;
-          ptx::mbar_wait(&w_full[ws], wphase);
-          if (split) ptx::mbar_wait(&w_full[ws1], ws1 == 0 ? wphase ^ 1 : wphase);
-          ptx::tc_fence_after();
-          const uint32_t w_hi = w_ring_lo + static_cast<uint32_t>(ws) * (kPkWSlotBytes >> 4);
-          const uint32_t w_lo = w_ring_lo + static_cast<uint32_t>(ws1) * (kPkWSlotBytes >> 4);
-          for (int i = 0; i < nb; ++i) {
-            const int as1 = (as + 1 == P.a_stages) ? 0 : as + 1;
-            if (!a_all) {
-              ptx::mbar_wait(&a_full[as], aphase);
-              if (split) ptx::mbar_wait(&a_full[as1], as1 == 0 ? aphase ^ 1 : aphase);
-              ptx::fence_proxy_async_smem();   // the activation stage was written with generic-proxy copies
-              ptx::tc_fence_after();
-            }
-            if (lane == 0 && t == cluster && kb + i - kb0 < 4) PK_TRACE(16 + kb + i - kb0);
-            const uint32_t a_hi = a_ring_lo + static_cast<uint32_t>(as) * a_step;
-            const uint32_t a_lo = a_ring_lo + static_cast<uint32_t>(as1) * a_step;
-            const bool first = (kb + i == kb0), last = (kb + i == kb1 - 1);
-            if (ptx::elect_one()) {
-              if (split) pkx::mma_block<true>(d0, d1, mtp, w_hi + i * blk_step, w_lo + i * blk_step, a_hi, a_lo, idesc, first);
-              else pkx::mma_block<false>(d0, d1, mtp, w_hi + i * blk_step, w_lo, a_hi, a_lo, idesc, first);
-              ptx::umma_commit(&a_empty[as]);
-              if (split) ptx::umma_commit(&a_empty[as1]);
-              if (i == nb - 1) { ptx::umma_commit(&w_empty[ws]); if (split) ptx::umma_commit(&w_empty[ws1]); }
-              if (last) ptx::umma_commit(&t_full[buf]);
+        if (a_all) {
+          // The whole K slab of the activations is in the ring: the weight slots of up to kPkChunk slot groups are awaited
+          // by different lanes at once (a try_wait on a completed barrier is ~90 cycles), then ONE elected thread issues
+          // every MMA and commit of the chunk back to back.  tools/mma_rate.cu: a 128 x (<= 64) x 16 MMA issues every 48
+          // cycles whatever its width or accumulator, a commit costs 45; the per-block waits, fences and elections of the
+          // first version made a 32-MMA tile 4500 cycles instead of ~2100.
+          const int planes = split ? 2 : 1;
+          int kb = kb0;
+          bool first_chunk = true;
+          while (kb < kb1) {
+            const int groups_left = (kb1 - kb + cps - 1) / cps;
+            int ng = groups_left < kPkChunk ? groups_left : kPkChunk;
+            if (ng * planes > P.w_slots) ng = P.w_slots / planes;
+            const int nsl = ng * planes;
+            if (lane < nsl) {
+              int j = ws + lane; uint32_t ph = wphase;
+              if (j >= P.w_slots) { j -= P.w_slots; ph ^= 1; }
+              ptx::mbar_wait(&w_full[j], ph);
             }
             __syncwarp();
-            if (split) { if (++as == P.a_stages) { as = 0; aphase ^= 1; } }
-            if (++as == P.a_stages) { as = 0; aphase ^= 1; }
+            ptx::tc_fence_after();
+            if (lane == 0 && t == cluster && first_chunk) PK_TRACE(16);
+            const int nblk = kb1 - kb < ng * cps ? kb1 - kb : ng * cps;
+            if (ptx::elect_one()) {
+              int lws = ws, las = as, lkb = kb;
+              for (int gi = 0; gi < ng; ++gi) {
+                const int nb = kb1 - lkb < cps ? kb1 - lkb : cps;
+                const int lws1 = (lws + 1 == P.w_slots) ? 0 : lws + 1;
+                const uint32_t w_hi = w_ring_lo + static_cast<uint32_t>(lws) * (kPkWSlotBytes >> 4);
+                const uint32_t w_lo = w_ring_lo + static_cast<uint32_t>(lws1) * (kPkWSlotBytes >> 4);
+                for (int i = 0; i < nb; ++i) {
+                  const int las1 = (las + 1 == P.a_stages) ? 0 : las + 1;
+                  const uint32_t a_hi = a_ring_lo + static_cast<uint32_t>(las) * a_step;
+                  const uint32_t a_lo = a_ring_lo + static_cast<uint32_t>(las1) * a_step;
+                  const bool first = (lkb + i == kb0), last = (lkb + i == kb1 - 1);
+                  if (split) pkx::mma_block<true>(d0, d1, mtp, w_hi + i * blk_step, w_lo + i * blk_step, a_hi, a_lo, idesc, first);
+                  else pkx::mma_block<false>(d0, d1, mtp, w_hi + i * blk_step, w_lo, a_hi, a_lo, idesc, first);
+                  ptx::umma_commit(&a_empty[las]);
+                  if (split) ptx::umma_commit(&a_empty[las1]);
+                  if (i == nb - 1) { ptx::umma_commit(&w_empty[lws]); if (split) ptx::umma_commit(&w_empty[lws1]); }
+                  if (last) ptx::umma_commit(&t_full[buf]);
+                  las = split ? ((las1 + 1 == P.a_stages) ? 0 : las1 + 1) : las1;
+                }
+                lws = split ? ((lws1 + 1 == P.w_slots) ? 0 : lws1 + 1) : lws1;
+                lkb += nb;
+              }
+            }
+            __syncwarp();
+            if (lane == 0 && t == cluster && first_chunk) PK_TRACE(17);
+            first_chunk = false;
+            as += nblk * planes;
+            if (as >= P.a_stages) { as -= P.a_stages; aphase ^= 1; }
+            ws += nsl;
+            if (ws >= P.w_slots) { ws -= P.w_slots; wphase ^= 1; }
+            kb += nblk;
           }
-          if (split) { if (++ws == P.w_slots) { ws = 0; wphase ^= 1; } }
-          if (++ws == P.w_slots) { ws = 0; wphase ^= 1; }
+        } else {
+          for (int kb = kb0; kb < kb1; kb += cps) {
+            const int nb = kb1 - kb < cps ? kb1 - kb : cps;
+            const int ws1 = (ws + 1 == P.w_slots) ? 0 : ws + 1;
+            ptx::mbar_wait(&w_full[ws], wphase);
+            if (split) ptx::mbar_wait(&w_full[ws1], ws1 == 0 ? wphase ^ 1 : wphase);
+            ptx::tc_fence_after();
+            const uint32_t w_hi = w_ring_lo + static_cast<uint32_t>(ws) * (kPkWSlotBytes >> 4);
+            const uint32_t w_lo = w_ring_lo + static_cast<uint32_t>(ws1) * (kPkWSlotBytes >> 4);
+            for (int i = 0; i < nb; ++i) {
+              const int as1 = (as + 1 == P.a_stages) ? 0 : as + 1;
+              if (!a_all) {
+                ptx::mbar_wait(&a_full[as], aphase);
+                if (split) ptx::mbar_wait(&a_full[as1], as1 == 0 ? aphase ^ 1 : aphase);
+                ptx::fence_proxy_async_smem();   // the activation stage was written with generic-proxy copies
+                ptx::tc_fence_after();
+              }
+              if (lane == 0 && t == cluster && kb + i - kb0 < 4) PK_TRACE(16 + kb + i - kb0);
+              const uint32_t a_hi = a_ring_lo + static_cast<uint32_t>(as) * a_step;
+              const uint32_t a_lo = a_ring_lo + static_cast<uint32_t>(as1) * a_step;
+              const bool first = (kb + i == kb0), last = (kb + i == kb1 - 1);
+              if (ptx::elect_one()) {
+                if (split) pkx::mma_block<true>(d0, d1, mtp, w_hi + i * blk_step, w_lo + i * blk_step, a_hi, a_lo, idesc, first);
+                else pkx::mma_block<false>(d0, d1, mtp, w_hi + i * blk_step, w_lo, a_hi, a_lo, idesc, first);
+                ptx::umma_commit(&a_empty[as]);
+                if (split) ptx::umma_commit(&a_empty[as1]);
+                if (i == nb - 1) { ptx::umma_commit(&w_empty[ws]); if (split) ptx::umma_commit(&w_empty[ws1]); }
+                if (last) ptx::umma_commit(&t_full[buf]);
+              }
+              __syncwarp();
+              if (split) { if (++as == P.a_stages) { as = 0; aphase ^= 1; } }
+              if (++as == P.a_stages) { as = 0; aphase ^= 1; }
+            }
+            if (split) { if (++ws == P.w_slots) { ws = 0; wphase ^= 1; } }
+            if (++ws == P.w_slots) { ws = 0; wphase ^= 1; }
+          }
         }
         tph ^= 1u << buf;
         if (++buf >= nbuf) buf = 0;
@@ -926,7 +983,7 @@ persistent_kernel(const __grid_constant__ PkParams P) {
         const int nbuf = MT <= 64 ? 2 : 1;
         if (have_k && buf >= nbuf) buf = 0;     // (the MMA warp does the same, and only for ops it takes part in)
         pkx::APieces ap;
-        pkx::a_pieces_init(ap, a_hi, lda, MT, wt);
+        pkx::a_pieces_init(ap, a_hi, lda, M, wt);   // rows M..MT-1 of a stage keep whatever they held: token columns nobody reads
         const long long lo_off = a_lo - a_hi;   // element offset of the lo plane (same layout)
         const Epilogue& e = g.epi;
         const bool lean = e.row_map == 0 && e.res_clip_rows == 0 && !e.pe && !e.gate && !e.drop_thr && !e.alpha_dev;
@@ -948,8 +1005,15 @@ persistent_kernel(const __grid_constant__ PkParams P) {
               if (ap.n <= 1) pkx::issue_slab<1>(ap, lo_off, split, kb0, kb1, as, P.a_stages, a_ring_addr, P.a_stage_bytes);
               else if (ap.n <= 3) pkx::issue_slab<3>(ap, lo_off, split, kb0, kb1, as, P.a_stages, a_ring_addr, P.a_stage_bytes);
               else pkx::issue_slab<8>(ap, lo_off, split, kb0, kb1, as, P.a_stages, a_ring_addr, P.a_stage_bytes);
+              // each thread waits for its own copies, then ONE lane per warp arrives for its 32 threads on every stage
+              // of the slab.  (cp.async.mbarrier.arrive.noinc per thread and stage cost ~100 ns apiece: 0.8 us of the
+              // 1.15 us slab phase at 8 stages, 1.6 us at 16 - whatever the number of bytes copied.)
+              if (wt == 0 && t == cluster) PK_TRACE(23);
+              asm volatile("cp.async.wait_all;" ::: "memory");
+              __syncwarp();
+              if (wt == 0 && t == cluster) PK_TRACE(24);
               for (int i = 0; i < a_need; ++i) {
-                pkx::a_block_arrive(a_full_addr + as * 8);
+                if (lane == 0) pkx::mbar_arrive_count(a_full_addr + as * 8, 32u);
                 if (++as == P.a_stages) { as = 0; aphase ^= 1; }
               }
             } else {

@@ -7,7 +7,7 @@ import sdvg_b200
 prec = sys.argv[1] if len(sys.argv) > 1 else "mixed"
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 cfg = sdvg_b200.CONFIGS["1_17_ball_complex_L1_64"]
-B, C, P = 8, 10, 10
+B, C, P = int(os.environ.get("C1_B", "8")), 10, 10
 torch.manual_seed(0)
 m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"], 0.1,
                           frame_size=64, precision=prec, max_clips=B, max_tokens=10, max_history=C + P).eval().cuda()
