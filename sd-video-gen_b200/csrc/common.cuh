@@ -58,6 +58,14 @@ struct Epilogue {
   int ln_in = 0;
   float2* stat_out = nullptr;
   int stat_ld = 0;
+  //  * small batches (stat_in != nullptr, together with ln_stats as the mode flag): no kernel turned the partials into
+  //    (mean, rstd) - every epilogue warp sums the stat_in_n slots of its 32 rows itself while its tile's main loop
+  //    runs (one launch less per LayerNorm where a launch is all latency; at large batch the 3 us kernel is cheaper
+  //    than the strided slot reads of every tile, profiles/README.md).  mean = sum * stat_inv_d,
+  //    rstd = rsqrt(max(sumsq * stat_inv_d - mean^2, 0) + stat_eps), as ln_stats_finalize_kernel.
+  const float2* stat_in = nullptr;
+  int stat_in_ld = 0, stat_in_n = 0;
+  float stat_inv_d = 0.f, stat_eps = 0.f;
   // training (backward GEMMs): alpha_dev multiplies like alpha but is read from device memory (1 / loss scale);
   // gate zeroes the value where gate[row][col] <= 0 (ReLU backward against the saved activation), before the residual
   const float* alpha_dev = nullptr;

@@ -141,8 +141,11 @@ class Engine {
   // epilogue leaves per-row partial sums in ln_part, the consumer reads the pre-norm planes through gamma-scaled weights
   bool use_fold = true;        // SDVG_LN_FOLD=0 disables (same-box A/B on B200: 50.0 -> 48.2 ms per C2 step, profiles/README.md round 2)
   int fold_min_rows = 1;       // (SDVG_LN_FOLD_MIN) also pays at small batch: C1 launch chain 872 -> 845 us per pass
-  float2* ln_part = nullptr;   // [max_rows][fold_ld]
+  float2* ln_part = nullptr;   // 2 x [max_rows][fold_ld]: producer n writes half n % 2 while it reads half (n - 1) % 2 (stat_in)
   int fold_ld = 0;
+  int ln_part_flip = 0;
+  float2* ln_part_w = nullptr; // the half the last stat_out GEMM wrote
+  int stats_inline_max = 128;  // (SDVG_STATS_INLINE_MAX) rows up to which the consumers sum the slots themselves (Epilogue::stat_in)
   int last_stat_slots = 0;     // column slots the last stat_out GEMM wrote per row (depends on its tile plan)
   int* pe_mod64 = nullptr;   // [max_clips] b mod 64
 
@@ -479,10 +482,11 @@ class Engine {
     if ((e = dalloc(&ln_stats, static_cast<size_t>(max_rows))) != cudaSuccess) return fail_cuda(e, "stats alloc");
     if (const char* v = std::getenv("SDVG_LN_FOLD")) use_fold = std::atoi(v) != 0;
     if (const char* v = std::getenv("SDVG_LN_FOLD_MIN")) fold_min_rows = std::atoi(v);   // (tests: fold at any size)
+    if (const char* v = std::getenv("SDVG_STATS_INLINE_MAX")) stats_inline_max = std::atoi(v);
     if (use_fold && tc() && !split_all() && d % 64 == 0 && max_rows >= fold_min_rows) {
       // every projection that reads a LayerNorm output gets gamma-scaled planes of its own (C2: +0.47 GB)
       fold_ld = 2 * ceil_div(d, 64);     // column slots per row: two epilogue warps per tile, tiles at least 64 wide
-      if ((e = dalloc(&ln_part, static_cast<size_t>(max_rows) * fold_ld)) != cudaSuccess) return fail_cuda(e, "fold partials alloc");
+      if ((e = dalloc(&ln_part, 2 * static_cast<size_t>(max_rows) * fold_ld)) != cudaSuccess) return fail_cuda(e, "fold partials alloc");
       auto add_fold = [&](Linear& L, const LNParam& norm) -> bool {
         if (L.split) return true;
         if (alloc_planes(L.pf, L.N, L.K, false, true) != cudaSuccess || dalloc(&L.fold_c, static_cast<size_t>(L.N)) != cudaSuccess ||
@@ -762,6 +766,7 @@ class Engine {
       if (!L.has_fold || split) return cudaErrorInvalidValue;
       e.ln_w = L.fold_c; e.ln_b = L.fold_c; e.bias = L.fold_b;
     }
+    if (e.stat_in && (plan.pair || plan.ks > 1 || !epilogue_vec4_ok(e, L.N))) return cudaErrorInvalidValue;
     if (e.stat_out) {
       if (plan.ks > 1 || !epilogue_vec4_ok(e, L.N)) return cudaErrorInvalidValue;
       last_stat_slots = ceil_div(L.N, plan.bn) * ((plan.pair || plan.bn >= 64) ? 2 : 1);
@@ -1162,12 +1167,19 @@ class Engine {
     const float* ptr = nullptr; int ld = 0;
     const float2* stats = nullptr; const float* w = nullptr; const float* b = nullptr;
     bool fold = false;
+    // small batch: the statistics are still the producer's partial sums (Epilogue::stat_in), `stats` is only the mode flag
+    const float2* slots = nullptr; int nslots = 0, slot_ld = 0; float inv_d = 0.f, eps = 0.f;
   };
+  static void stats_from(Epilogue& e, const ResSrc& rs) {
+    e.ln_stats = rs.stats;
+    e.stat_in = rs.slots; e.stat_in_n = rs.nslots; e.stat_in_ld = rs.slot_ld; e.stat_inv_d = rs.inv_d; e.stat_eps = rs.eps;
+  }
   static void operand_from(Epilogue& e, const ResSrc& rs) {
-    if (rs.fold) { e.ln_in = 1; e.ln_stats = rs.stats; }
+    if (rs.fold) { e.ln_in = 1; stats_from(e, rs); }
   }
   static void residual_from(Epilogue& e, const ResSrc& rs) {
-    e.residual = rs.ptr; e.ld_res = rs.ld; e.ln_stats = rs.stats; e.ln_w = rs.w; e.ln_b = rs.b;
+    e.residual = rs.ptr; e.ld_res = rs.ld; e.ln_w = rs.w; e.ln_b = rs.b;
+    stats_from(e, rs);
   }
 
   cudaError_t run_model(int B, int Ss, int St, bool same, int mask_kind, const float* mask, const int* pe_index,
@@ -1191,15 +1203,22 @@ class Engine {
     auto fold_here = [&](int M, bool allow_lazy) { return use_fold && lazy && allow_lazy && !pk_rec && M >= fold_min_rows; };
     auto fold_outputs = [&](Epilogue& e, const ActBuf& x_out) {
       e.out_hi = x_out.p.hi; e.out_lo = nullptr; e.ld16 = x_out.p.ld;
-      e.stat_out = ln_part; e.stat_ld = fold_ld;
+      ln_part_w = ln_part + static_cast<size_t>(ln_part_flip) * max_rows * fold_ld;
+      ln_part_flip ^= 1;
+      e.stat_out = ln_part_w; e.stat_ld = fold_ld;
     };
     auto norm_to = [&](int M, int S, const LNParam& norm, const ActBuf& x_out, bool allow_lazy, ResSrc& out_rs) -> cudaError_t {
       if (fold_here(M, allow_lazy)) {
         // (measured: rebuilding the statistics from the partials inside the consumers' epilogues instead of this 3 us
         // kernel costs more than it saves - 22 strided 8-byte loads per row and tile: +2.7 ms per C2 step)
         out_rs = ResSrc{ybuf.f32, ybuf.ld32, ln_stats, norm.w, norm.b, true};
+        if (M <= stats_inline_max) {   // a launch is all latency here: the consumers' epilogue warps add the slots themselves
+          out_rs.slots = ln_part_w; out_rs.nslots = last_stat_slots; out_rs.slot_ld = fold_ld;
+          out_rs.inv_d = 1.0f / static_cast<float>(d); out_rs.eps = cfg.layer_norm_eps;
+          return cudaSuccess;
+        }
         Scope sc(this, KC_LN, 0.0, double(M) * last_stat_slots * 8.0, st);
-        return launch_ln_stats_finalize(ln_part, fold_ld, last_stat_slots, M, d, cfg.layer_norm_eps, ln_stats, st);
+        return launch_ln_stats_finalize(ln_part_w, fold_ld, last_stat_slots, M, d, cfg.layer_norm_eps, ln_stats, st);
       }
       if (lazy && allow_lazy) {
         out_rs = ResSrc{ybuf.f32, ybuf.ld32, ln_stats, norm.w, norm.b};

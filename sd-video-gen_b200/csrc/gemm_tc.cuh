@@ -158,7 +158,21 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmArgs& args, int
     const int row = row0 + lane;
     int rrow = row;
     if constexpr (FANCY) rrow = epi_res_row(args.epi, row);
-    pre.st[lane] = row < args.M ? __ldg(args.epi.ln_stats + rrow) : make_float2(0.f, 0.f);
+    float2 stv = make_float2(0.f, 0.f);
+    if (row < args.M) {
+      if (args.epi.stat_in) {   // small batch: the row's partial sums straight from the producer's epilogue slots
+        const float2* p = args.epi.stat_in + static_cast<size_t>(rrow) * args.epi.stat_in_ld;
+        const int n = args.epi.stat_in_n;
+        float s = 0.f, q = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) { const float2 v = __ldcg(p + i); s += v.x; q += v.y; }
+        const float mean = s * args.epi.stat_inv_d;
+        stv = make_float2(mean, rsqrtf(fmaxf(q * args.epi.stat_inv_d - mean * mean, 0.f) + args.epi.stat_eps));
+      } else {
+        stv = __ldg(args.epi.ln_stats + rrow);
+      }
+    }
+    pre.st[lane] = stv;
     __syncwarp();
   }
 #pragma unroll
