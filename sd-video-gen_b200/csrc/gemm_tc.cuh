@@ -437,6 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform (see gemm_tc2.cuh)
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { SDVG_TRACE(0); if (args.trace && blockIdx.x == 0) args.trace[40] = clock64(); }
   const int M = args.M, N = args.N, K = args.K;
   const int m_tiles = (M + kTcBM - 1) / kTcBM;
   const int n_tiles = (N + BN - 1) / BN;
@@ -474,8 +475,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only smem / TMEM / kernel parameters: it may overlap the previous kernel's tail
+  if (threadIdx.x == 0) SDVG_TRACE(1);
   pdl_wait();
   pdl_trigger();
+  if (threadIdx.x == 0) SDVG_TRACE(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
@@ -496,6 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (SPLIT) ptx::tma_load_2d(sp + Cfg::kABytes, &tmA_lo, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
           ptx::tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kTcBK, n_blk * BN);
           if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &tmB_lo, &full_bar[stage], kb * kTcBK, n_blk * BN);
+          if (t == cta && kb == kb0) SDVG_TRACE(3);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -513,31 +517,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
       const uint32_t d1 = d0 + BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
-        const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
-        const uint64_t b_hi = ptx::make_kmajor_sw128_desc(sb);
-        const uint64_t a_lo = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
-        const uint64_t b_lo = ptx::make_kmajor_sw128_desc(sb + Cfg::kBBytes);
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kTcBK / 16; ++k) {
-            const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
-            const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B = 2 << 4
-            ptx::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
-            if (SPLIT) {
-              ptx::umma_f16(d1, a_hi + adv, b_lo + adv, idesc, acc);
-              ptx::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+      if constexpr (BN <= 64) {
+        // Stages are consumed in batches: lane l tests the barrier of stage (stage + l), the batch is the run of stages
+        // that are already full (at least one: then the warp blocks on it), and ONE elected thread issues every MMA and
+        // commit of the batch back to back.  With narrow tiles an MMA executes in 48 cycles (tools/mma_rate.cu) while one
+        // wait + fence + election + descriptor set-up per K block cost ~315: the K loop of a 40 x 2048 x 2048 GEMM was 5.4 us
+        // of its 8.2 us launch (tools/gemm_trace.py).
+        constexpr int kBatch = Cfg::kStages < 4 ? Cfg::kStages : 4;
+        const uint32_t ring_lo = ptx::kmajor_sw128_desc_lo(ptx::smem_u32(stage_base));
+        int kb = kb0;
+        while (kb < kb1) {
+          int want = kb1 - kb < kBatch ? kb1 - kb : kBatch;
+          bool ready = false;
+          if (lane < want) {
+            int s2 = stage + lane; uint32_t ph = phase;
+            if (s2 >= Cfg::kStages) { s2 -= Cfg::kStages; ph ^= 1; }
+            ready = ptx::mbar_test_wait(&full_bar[s2], ph);
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, ready);
+          int nst = __ffs(~mask) - 1;                 // leading run of full stages
+          if (nst > want) nst = want;
+          if (nst == 0) { ptx::mbar_wait(&full_bar[stage], phase); nst = 1; }
+          ptx::tc_fence_after();
+          if (t == cta && lane == 0 && kb == kb0) SDVG_TRACE(8);
+          if (ptx::elect_one()) {
+            int st = stage;
+            for (int j = 0; j < nst; ++j) {
+              const uint32_t a_hi = ring_lo + static_cast<uint32_t>(st) * (Cfg::kStageBytes >> 4);
+              const uint32_t b_hi = a_hi + ((Cfg::kPlanes * Cfg::kABytes) >> 4);
+              const uint32_t a_lo = a_hi + (Cfg::kABytes >> 4);
+              const uint32_t b_lo = b_hi + (Cfg::kBBytes >> 4);
+  #pragma unroll
+              for (int k = 0; k < kTcBK / 16; ++k) {
+                const uint32_t acc = (kb + j != kb0 || k != 0) ? 1u : 0u;
+                const uint32_t adv = static_cast<uint32_t>(k * 2);  // 16 elements * 2 B = 32 B = 2 << 4
+                ptx::umma_f16_lo(d0, a_hi + adv, b_hi + adv, idesc, acc);
+                if (SPLIT) {
+                  ptx::umma_f16_lo(d1, a_hi + adv, b_lo + adv, idesc, acc);
+                  ptx::umma_f16_lo(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+              }
+              ptx::umma_commit(&empty_bar[st]);                              // smem stage reusable once these MMAs retire
+              if (kb + j == kb1 - 1) {
+                ptx::umma_commit(&tfull_bar[buf]);                           // accumulator(s) of this tile complete
+                if (t == cta) SDVG_TRACE(16);
+              }
+              if (++st == Cfg::kStages) st = 0;
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);                         // smem stage reusable once these MMAs retire
-          if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[buf]);        // accumulator(s) of this tile complete
+          __syncwarp();
+          stage += nst;
+          if (stage >= Cfg::kStages) { stage -= Cfg::kStages; phase ^= 1; }
+          kb += nst;
         }
-        __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      } else {   // wide tiles: an MMA outlasts its issue, one blocking wait per stage is cheaper (C2 step: 49.37 vs 49.51 ms)
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(stage_base + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kPlanes * Cfg::kABytes;
+          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(sa);
+          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(sb);
+          const uint64_t a_lo = ptx::make_kmajor_sw128_desc(sa + Cfg::kABytes);
+          const uint64_t b_lo = ptx::make_kmajor_sw128_desc(sb + Cfg::kBBytes);
+          if (ptx::elect_one()) {
+  #pragma unroll
+            for (int k = 0; k < kTcBK / 16; ++k) {
+              const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
+              const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B = 2 << 4
+              ptx::umma_f16(d0, a_hi + adv, b_hi + adv, idesc, acc);
+              if (SPLIT) {
+                ptx::umma_f16(d1, a_hi + adv, b_lo + adv, idesc, acc);
+                ptx::umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);                         // smem stage reusable once these MMAs retire
+            if (kb == kb1 - 1) ptx::umma_commit(&tfull_bar[buf]);        // accumulator(s) of this tile complete
+          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
       }
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
@@ -573,6 +632,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_epilogue_prefetch<FANCY, NCW, PF>(args, row0, n_blk * BN, lane, c0, pre);
       ptx::mbar_wait(&tfull_bar[buf], buf_phase);
       ptx::tc_fence_after();
+      if (t == cta && warp == 2 && lane == 0) SDVG_TRACE(24);
       const float* part_row = nullptr;
       const unsigned int expected = static_cast<unsigned int>(Cfg::kEpiActive * (ks - 1));
       if (ks > 1) {
@@ -596,15 +656,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // the last reader of this tile's partials re-arms the flag for the next launch
         if (atomicAdd(args.ks_flags + t, 1u) == expected + Cfg::kEpiActive - 1) args.ks_flags[t] = 0u;
       }
+      if (t == cta && warp == 2 && lane == 0) SDVG_TRACE(32);
       if (++buf == 2) { buf = 0; buf_phase ^= 1; }
     }
   }
 
   __syncthreads();
+  if (threadIdx.x == 0) SDVG_TRACE(4);
   if (warp == 1) {
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 0) { SDVG_TRACE(5); if (args.trace && blockIdx.x == 0) args.trace[41] = clock64(); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side

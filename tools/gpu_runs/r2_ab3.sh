@@ -1,0 +1,12 @@
+: > gpurun_out/t_ab3.log
+for i in 1 2; do
+for v in old new; do
+cp tools/scratch/variants/libsdvg_$v.so sd-video-gen_b200/libsdvg.so; touch sd-video-gen_b200/libsdvg.so
+timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('$v',d['value'],d['ms_per_step'],d['roofline']['classes_ms'])" >> gpurun_out/t_ab3.log
+done
+done
+cp tools/scratch/variants/libsdvg_new.so sd-video-gen_b200/libsdvg.so; touch sd-video-gen_b200/libsdvg.so
+timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | grep -E "^E  |passed|failed|Error" | head -30 >> gpurun_out/t_ab3.log
+SDVG_PK=0 timeout 200 python tools/c1_chain.py mixed 2>&1 | grep "us per pass" >> gpurun_out/t_ab3.log
+SDVG_PK=0 C1_B=1 timeout 200 python tools/c1_chain.py mixed 2>&1 | grep "us per pass" >> gpurun_out/t_ab3.log
