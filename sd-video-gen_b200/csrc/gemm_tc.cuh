@@ -31,12 +31,18 @@ constexpr int kTcEpiWarps = 8;
 constexpr int kTcEpiStride = 36;  // floats; 32x32 transpose tile, padded to keep 128-bit accesses conflict-free
 constexpr int kTcSmemLimit = 232448;  // 227 KB
 
-template <int BN, bool SPLIT>
+// AROWS: rows of shared memory a stage keeps for the A operand.  128 = the whole UMMA tile.  48 (small batches, every
+// token row fits the 48-row TMA box): the MMA still reads 128 rows from the stage's base - rows 48..127 are whatever
+// follows in shared memory (the B tile, the next stages) and only feed accumulator rows >= M, which no epilogue stores -
+// and the ring gets twice the stages.  A narrow-tile launch is bound by the bytes one SM keeps in flight (8 stages of
+// 6 + 4 KB against ~1 us of HBM latency): C1 launch chain 808.6 us per pass with 8 stages, 799.5 with 9 (same box).
+template <int BN, bool SPLIT, int AROWS = 128>
 struct TcCfg {
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
   static_assert(!(SPLIT && BN == 256), "split mode needs two accumulators per tile: BN <= 128");
+  static_assert(AROWS == 128 || (AROWS % 8 == 0 && !SPLIT && BN <= 64), "compact A stages: one-plane narrow tiles only");
   static constexpr int kPlanes = SPLIT ? 2 : 1;
-  static constexpr int kABytes = kTcBM * kTcBK * 2;
+  static constexpr int kABytes = AROWS * kTcBK * 2;
   static constexpr int kBBytes = BN * kTcBK * 2;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kEpiBytes = kTcEpiWarps * 32 * kTcEpiStride * 4 + kTcEpiWarps * 32 * 8;   // transpose tiles + (mean, rstd) of each warp's 32 rows
@@ -44,12 +50,15 @@ struct TcCfg {
   static constexpr int kEpiActive = BN >= 64 ? 8 : 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxStages = (kTcSmemLimit - 1024 /*align slack*/ - kEpiBytes - kBarBytes) / kStageBytes;
-  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kStageCap = AROWS < 128 ? 16 : (BN <= 32 ? 12 : 8);   // narrow tiles (small M) are bound by the bytes in flight per SM
+  static constexpr int kStages = kMaxStages > kStageCap ? kStageCap : kMaxStages;
   static constexpr int kColsPerTile = BN * kPlanes;
   static constexpr int kTmemCols = (2 * kColsPerTile) < 32 ? 32 : (2 * kColsPerTile);
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + kBarBytes;
   static_assert(kStages >= 2, "pipeline depth");
   static_assert(kTmemCols <= 512, "TMEM");
+  // the last stage's 128-row A read stays inside the allocation
+  static_assert(kStageBytes + kEpiBytes + kBarBytes >= 128 * kTcBK * 2, "A overrun");
 };
 
 __device__ __forceinline__ unsigned long long global_timer() {
@@ -418,12 +427,12 @@ inline bool epilogue_is_fancy(const Epilogue& e) {
          e.gate != nullptr || e.drop_thr != 0;
 }
 
-template <int BN, bool SPLIT, bool FANCY>
+template <int BN, bool SPLIT, bool FANCY, int AROWS = 128>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ TcGemmArgs args) {
-  using Cfg = TcCfg<BN, SPLIT>;
+  using Cfg = TcCfg<BN, SPLIT, AROWS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -716,16 +725,22 @@ inline bool epilogue_vec4_ok(const Epilogue& e, int N) {
   return true;
 }
 
-template <int BN, bool SPLIT, bool FANCY>
+constexpr int kTcCompactRows = 48;   // compact A stages (TcCfg AROWS) when every token row fits the 48-row TMA box
+
+template <int BN, bool SPLIT, bool FANCY, int AROWS = 128>
 inline cudaError_t launch_gemm_tc_f(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                                     const CUtensorMap& b_lo, const TcGemmArgs& args, int num_sms,
                                     cudaStream_t stream) {
-  using Cfg = TcCfg<BN, SPLIT>;
+  if constexpr (AROWS == 128 && !SPLIT && BN <= 64) {
+    if (args.M <= kTcCompactRows && args.a_box_rows > 0 && args.a_box_rows <= kTcCompactRows && args.ksplit <= 1)
+      return launch_gemm_tc_f<BN, SPLIT, FANCY, kTcCompactRows>(a_hi, a_lo, b_hi, b_lo, args, num_sms, stream);
+  }
+  using Cfg = TcCfg<BN, SPLIT, AROWS>;
   static bool attr_set[64] = {};  // the attribute is per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT, FANCY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT, FANCY, AROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
@@ -740,7 +755,7 @@ inline cudaError_t launch_gemm_tc_f(const CUtensorMap& a_hi, const CUtensorMap& 
   }
   TcGemmArgs a2 = args;
   a2.vec4 = epilogue_vec4_ok(args.epi, args.N) ? 1 : 0;
-  return launch_kernel(gemm_tc_kernel<BN, SPLIT, FANCY>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, a_hi, a_lo, b_hi, b_lo, a2);
+  return launch_kernel(gemm_tc_kernel<BN, SPLIT, FANCY, AROWS>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, a_hi, a_lo, b_hi, b_lo, a2);
 }
 
 template <int BN, bool SPLIT>
