@@ -50,7 +50,7 @@ struct TcCfg {
   static constexpr int kEpiActive = BN >= 64 ? 8 : 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kMaxStages = (kTcSmemLimit - 1024 /*align slack*/ - kEpiBytes - kBarBytes) / kStageBytes;
-  static constexpr int kStageCap = AROWS < 128 ? 16 : (BN <= 32 ? 12 : 8);   // narrow tiles (small M) are bound by the bytes in flight per SM
+  static constexpr int kStageCap = AROWS < 128 ? 16 : 8;   // small-M launches are bound by the bytes in flight per SM
   static constexpr int kStages = kMaxStages > kStageCap ? kStageCap : kMaxStages;
   static constexpr int kColsPerTile = BN * kPlanes;
   static constexpr int kTmemCols = (2 * kColsPerTile) < 32 ? 32 : (2 * kColsPerTile);
@@ -508,7 +508,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (SPLIT) ptx::tma_load_2d(sp + Cfg::kABytes, &tmA_lo, &full_bar[stage], kb * kTcBK, m_blk * kTcBM);
           ptx::tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kTcBK, n_blk * BN);
           if (SPLIT) ptx::tma_load_2d(sb + Cfg::kBBytes, &tmB_lo, &full_bar[stage], kb * kTcBK, n_blk * BN);
-          if (t == cta && kb == kb0) SDVG_TRACE(3);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -526,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t d0 = tmem_base + buf * Cfg::kColsPerTile;
       const uint32_t d1 = d0 + BN;
-      if constexpr (BN <= 64) {
+      if constexpr (AROWS < 128) {   // (at 49..128 rows the batched loop measured 3-4 % SLOWER than one blocking wait per stage)
         // Stages are consumed in batches: lane l tests the barrier of stage (stage + l), the batch is the run of stages
         // that are already full (at least one: then the warp blocks on it), and ONE elected thread issues every MMA and
         // commit of the batch back to back.  With narrow tiles an MMA executes in 48 cycles (tools/mma_rate.cu) while one
@@ -548,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (nst > want) nst = want;
           if (nst == 0) { ptx::mbar_wait(&full_bar[stage], phase); nst = 1; }
           ptx::tc_fence_after();
-          if (t == cta && lane == 0 && kb == kb0) SDVG_TRACE(8);
+          if (kb == kb0 && t == cta && lane == 0) SDVG_TRACE(8);
           if (ptx::elect_one()) {
             int st = stage;
             for (int j = 0; j < nst; ++j) {
@@ -579,7 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (stage >= Cfg::kStages) { stage -= Cfg::kStages; phase ^= 1; }
           kb += nst;
         }
-      } else {   // wide tiles: an MMA outlasts its issue, one blocking wait per stage is cheaper (C2 step: 49.37 vs 49.51 ms)
+      } else {   // full-height stages / wide tiles: one blocking wait per stage is cheaper (C2 step: 49.37 vs 49.51 ms)
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();

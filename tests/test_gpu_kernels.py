@@ -96,3 +96,24 @@ def test_split_k_small_m_gemm(precision):
             assert torch.equal(C1, C2), (M, N, K, bn, ks)
         C0, _ = sdvg_b200.gemm(A, W, b, relu=True, precision=precision)            # automatic plan (split-K when it pays)
         assert relerr(C0, want) < TOL[precision], (M, N, K)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(40, 2048, 2048), (5, 2048, 2048), (48, 520, 1024), (17, 96, 4096), (1, 64, 192)])
+def test_small_batch_gemm_compact_stages(precision, shape):
+    """M <= 48 token rows: the one-CTA kernel's narrow tiles keep 48-row A stages (the MMA reads 128 rows from the stage
+    base, the surplus rows feed accumulator rows nobody stores) in a ring of up to 16 stages, and issue their MMAs in
+    batches.  Against float64, and bit-identical to the same rows computed inside a 128-row problem (full-height stages)."""
+    import sdvg_b200
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 11 + N)
+    A = torch.randn(128, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    for bn in (32, 64):
+        if bn > 32 and bn > N:
+            continue
+        small, _ = sdvg_b200.gemm(A[:M].contiguous(), W, b, precision=precision, block_n=bn)
+        full, _ = sdvg_b200.gemm(A, W, b, precision=precision, block_n=bn)
+        assert relerr(small, ref(A[:M], W, b, False, precision)) < TOL[precision]
+        assert torch.equal(small, full[:M])

@@ -500,3 +500,23 @@ def test_layernorm_folded_into_the_gemms(monkeypatch):
     for prec in ("mixed", "fp16"):
         assert not torch.equal(outs["0", prec], outs["1", prec])                         # the folded path really ran
         assert R.max_rel_per_frame(outs["1", prec, "big"], outs["0", prec, "big"])[0] < TOL16
+
+
+def test_folded_layernorm_statistics_inline_vs_statistics_kernel(monkeypatch):
+    """Up to 128 token rows the consumers of a folded LayerNorm add the producer's partial sums themselves
+    (Epilogue::stat_in, SDVG_STATS_INLINE_MAX); above that a statistics kernel does.  Same partial sums, different summation
+    order: the two paths agree to fp32 rounding through the 16-bit pipeline, both within the golden tolerance, and the
+    small-batch result does not depend on which rollouts ran before (double-buffered slots)."""
+    g = load_golden("small_rollout")
+    ctx = g["ctx"].to(DEV)
+    n = g["free5"].shape[1]
+    outs = {}
+    for inline in ("128", "0"):
+        monkeypatch.setenv("SDVG_STATS_INLINE_MAX", inline)
+        m, _ = ours_from(g, "mixed")
+        a = sdvg_b200.rollout(m, ctx, n, 5, teacher=g["free5"].to(DEV)).cpu()
+        b = sdvg_b200.rollout(m, ctx, n, 5, teacher=g["free5"].to(DEV)).cpu()
+        assert torch.equal(a, b), inline
+        assert R.max_rel_per_frame(a, g["free5"]).max() < TOL16, inline
+        outs[inline] = a
+    assert R.max_rel_per_frame(outs["128"], outs["0"]).max() < 2e-3

@@ -13,7 +13,7 @@ if len(sys.argv) > 2:
     os.environ["SDVG_GRAPH"] = sys.argv[2]
 os.environ.setdefault("SDVG_PK", "0")
 cfg = sdvg_b200.CONFIGS["1_17_ball_complex_L1_64"]
-B, C, P, W = int(os.environ.get("C1_B", "8")), 10, 10, 5
+B, C, P, W = int(os.environ.get("C1_B", "8")), 10, 10, int(os.environ.get("C1_W", "5"))
 torch.manual_seed(0)
 m = sdvg_b200.Transformer(0, cfg["dim_model"], cfg["num_heads"], cfg["num_encoder_layers"], cfg["num_decoder_layers"], 0.1,
                           frame_size=64, precision=prec, max_clips=B, max_tokens=10, max_history=C + P).eval().cuda()

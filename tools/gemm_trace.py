@@ -23,9 +23,10 @@ t0 = t[0]
 names = {0: "entry", 1: "prologue done", 2: "pdl_wait passed", 3: "first TMA issued", 4: "main work done (CTA0)", 5: "exit"}
 print(f"{prec} {M}x{N}x{K} bn={bn}: event-timed {ms*1e3:.1f} us (single launch incl. launch latency)")
 for i in (0, 1, 2, 3):
-    print(f"  {names[i]:28s} {(t[i]-t0)/1e3:8.2f} us")
+    if t[i]:
+        print(f"  {names[i]:28s} {(t[i]-t0)/1e3:8.2f} us")
 for i in range(8):
-    if t[8 + i]:
+    if t[8 + i] and t[16 + i]:
         print(f"  tile {i}: first stage full {(t[8+i]-t0)/1e3:8.2f}  mma issued {(t[16+i]-t0)/1e3:8.2f}  "
               f"acc ready {(t[24+i]-t0)/1e3:8.2f}  epilogue done {(t[32+i]-t0)/1e3:8.2f} us")
 for i in (4, 5):
