@@ -237,16 +237,18 @@ def run_extras(a, model_c2, world, rank, local, dev):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = model.launch_count()
+        # a small-batch rollout is ~10 ms: a few steps from an idle queue mostly time the clocks ramping up
+        steps = K if B * W > 512 else max(K, 12)
         e0.record()
-        for _ in range(K):
+        for _ in range(steps):
             step()
         e1.record()
         sync()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item()) / K
-        launches = (model.launch_count() - n0) // K
+        ms = float(ms.item()) / steps
+        launches = (model.launch_count() - n0) // steps
         clocks = sampler.stop() if rank == 0 else None
         model.timing(True)
         model.timing_read()
@@ -258,7 +260,7 @@ def run_extras(a, model_c2, world, rank, local, dev):
         n_param = sum(p.numel() for k, p in model.named_parameters() if p.dim() == 2)
         wbytes = prof["persistent"]["bytes"] / P if prof["persistent"]["launches"] else n_param * (4.0 if precision == "fp32" else 2.0)
         r = {"workload": f"{cfg_name} rollout: {B} clips/GPU x {world} GPU, {C} ctx -> {P} pred, window {W}, {precision}",
-             "frames_per_s": world * B * P / (ms * 1e-3), "ms_per_rollout": ms, "ms_per_pass": ms / P, "steps": K, "warmup": WARM + 1,
+             "frames_per_s": world * B * P / (ms * 1e-3), "ms_per_rollout": ms, "ms_per_pass": ms / P, "steps": steps, "warmup": WARM + 1,
              "launches_per_rollout": int(launches), "clocks": clocks,
              "step_tflops_executed": flops / (ms * 1e-3) / 1e12,
              "frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / pk["tflops"],
